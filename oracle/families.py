@@ -1,0 +1,98 @@
+"""oracle/families.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+NumPy restatements of the closed nonlinear-constraint families the CUDA engine
+evaluates on device (sco_py_b200/csrc/sco_families.cuh).  In the reference these
+are user-supplied black-box callables handed to `Expr(f, grad)`
+(sco_py/expr.py:22-25); SURVEY.md section 8(d) fixes the concrete functions of
+the benchmark configurations.  Every function takes x of shape (n, 1) and
+returns f of shape (m, 1) / J of shape (m, n), the contract of expr.py:34-41
+and expr.py:78-100.
+"""
+import numpy as np
+
+# ---------------------------------------------------------------- QUADFORM (C4)
+
+
+def tri_index(n):
+    """Row-major packed upper-triangle index pairs (r <= c)."""
+    r, c = np.triu_indices(n)
+    return r, c
+
+
+def unpack_sym(packed, n):
+    """packed (..., n(n+1)/2) -> symmetric (..., n, n)."""
+    r, c = tri_index(n)
+    out = np.zeros(packed.shape[:-1] + (n, n))
+    out[..., r, c] = packed
+    out[..., c, r] = packed
+    return out
+
+
+def pack_sym(S):
+    n = S.shape[-1]
+    r, c = tri_index(n)
+    return S[..., r, c]
+
+
+def quadform_f(x, Pm, a):
+    """f_j = 0.5 x'P_j x + a_j'x ;  Pm (m, n, n) symmetric, a (m, n)."""
+    xv = x[:, 0]
+    Px = Pm @ xv  # (m, n)
+    return (0.5 * Px @ xv + a @ xv)[:, None]
+
+
+def quadform_grad(x, Pm, a):
+    return Pm @ x[:, 0] + a
+
+
+# ---------------------------------------------------------------- CIRCLE2D (C2)
+
+
+def circle_f(x, centers, radii, T):
+    """Row t*K+k: R_k - ||p_t - c_k||, p_t = x[2t:2t+2]."""
+    p = x[:, 0].reshape(T, 2)
+    d = p[:, None, :] - centers[None, :, :]  # (T, K, 2)
+    dist = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1])
+    return (radii[None, :] - dist).reshape(-1, 1)
+
+
+def circle_grad(x, centers, radii, T):
+    K = centers.shape[0]
+    p = x[:, 0].reshape(T, 2)
+    d = p[:, None, :] - centers[None, :, :]
+    dist = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1])
+    J = np.zeros((T * K, 2 * T))
+    for t in range(T):
+        for k in range(K):
+            J[t * K + k, 2 * t] = -d[t, k, 0] / dist[t, k]
+            J[t * K + k, 2 * t + 1] = -d[t, k, 1] / dist[t, k]
+    return J
+
+
+# ---------------------------------------------------------------- FK7 (C3)
+# Modified-DH (Craig) chain, Franka-like constants; position of the flange.
+FK7_A = np.array([0.0, 0.0, 0.0, 0.0825, -0.0825, 0.0, 0.088])
+FK7_D = np.array([0.333, 0.0, 0.316, 0.0, 0.384, 0.0, 0.0])
+FK7_ALPHA = np.array([0.0, -np.pi / 2, np.pi / 2, np.pi / 2, -np.pi / 2, np.pi / 2, np.pi / 2])
+FK7_FLANGE = 0.107
+
+
+def fk7_pos(qj):
+    """qj (7,) -> (3,) flange position.  T_i = Rx(alpha_i) Tx(a_i) Rz(q_i) Tz(d_i)."""
+    R = np.eye(3)
+    p = np.zeros(3)
+    for i in range(7):
+        ca, sa = np.cos(FK7_ALPHA[i]), np.sin(FK7_ALPHA[i])
+        ct, st = np.cos(qj[i]), np.sin(qj[i])
+        Ri = np.array([[ct, -st, 0.0],
+                       [st * ca, ct * ca, -sa],
+                       [st * sa, ct * sa, ca]])
+        pi = np.array([FK7_A[i], -sa * FK7_D[i], ca * FK7_D[i]])
+        p = p + R @ pi
+        R = R @ Ri
+    return p + R @ np.array([0.0, 0.0, FK7_FLANGE])
+
+
+def fk7_f(x):
+    """Rows 0..2: flange position for the joints of the LAST time-step (x[-7:])."""
+    return fk7_pos(x[-7:, 0]).reshape(3, 1)
