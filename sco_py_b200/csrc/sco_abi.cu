@@ -1,0 +1,617 @@
+// sco_abi.cu -- kernels + the C ABI declared in include/sco_b200.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+//        -Iinclude sco_py_b200/csrc/sco_abi.cu -o sco_py_b200/libsco_b200.so
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "sco_b200.h"
+#include "sco_device.cuh"
+#include "sco_families.cuh"
+#include "sco_qp.cuh"
+#include "sco_sqp.cuh"
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(SCO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                    \
+  } while (0)
+
+extern "C" const char *sco_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------ kernels
+template <int TEAM>
+__global__ void __launch_bounds__(TEAM)
+k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st, long long B,
+        const double *__restrict__ params, const double *__restrict__ x0, double *__restrict__ x_out,
+        int *__restrict__ verdict, double *__restrict__ merit, double *__restrict__ objective,
+        double *__restrict__ max_vio, int *__restrict__ stats, double *__restrict__ Jscr,
+        unsigned long long *counter) {
+  extern __shared__ double sm[];
+  __shared__ long long next;
+  QPW w;
+  w.bind(sm, S.L);
+  double *xc = sm + S.L.total;  // n doubles appended after the layout
+  double *Jg = Jscr + (size_t)blockIdx.x * S.jnnz;
+  const int tid = threadIdx.x;
+  while (true) {
+    if (tid == 0) next = (long long)atomicAdd(counter, 1ull);
+    Team<TEAM>::sync();
+    const long long b = next;
+    Team<TEAM>::sync();
+    if (b >= B) break;
+    const double *prm = params + b * S.stride;
+    SqpSolver<TEAM> sq(S, st, w, prm, xc, Jg);
+    SqpOut o = sq.run(x0 + b * S.n);
+    for (int j = tid; j < S.n; j += TEAM) x_out[b * S.n + j] = xc[j];
+    if (tid == 0) {
+      verdict[b] = o.verdict;
+      if (merit) merit[b] = o.merit;
+      if (objective) objective[b] = o.objective;
+      if (max_vio) max_vio[b] = o.max_vio;
+      if (stats) {
+        stats[4 * b] = o.sqp_iters; stats[4 * b + 1] = o.qp_solves;
+        stats[4 * b + 2] = o.admm_iters; stats[4 * b + 3] = o.last_status;
+      }
+    }
+    Team<TEAM>::sync();
+  }
+}
+
+template <int TEAM>
+__global__ void __launch_bounds__(TEAM)
+k_convexify(const __grid_constant__ DevStruct S, long long B, const double *__restrict__ params,
+            const double *__restrict__ x, double *__restrict__ f, double *__restrict__ J,
+            double *__restrict__ bvec, double *__restrict__ obj, double *__restrict__ Jscr) {
+  extern __shared__ double sm[];
+  QPW w;
+  w.bind(sm, S.L);
+  double *xc = sm + S.L.total;
+  const int tid = threadIdx.x;
+  DevSettings st;
+  memset(&st, 0, sizeof(st));
+  st.freeze_sparsity = 1;
+  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+    const double *prm = params + b * S.stride;
+    double *Jg = J ? J + b * S.jnnz : Jscr + (size_t)blockIdx.x * S.jnnz;
+    SqpSolver<TEAM> sq(S, st, w, prm, xc, Jg);
+    for (int j = tid; j < S.n; j += TEAM) xc[j] = x[b * S.n + j];
+    Team<TEAM>::sync();
+    bool mask_set = false;
+    sq.convexify(mask_set);
+    for (int i = tid; i < S.m_nl; i += TEAM) {
+      if (f) f[b * S.m_nl + i] = w.fv[i];
+      if (bvec) bvec[b * S.m_nl + i] = w.bb[i];
+    }
+    if (obj) {
+      const double ov = sq.objective();
+      if (tid == 0) obj[b] = ov;
+    }
+    Team<TEAM>::sync();
+  }
+}
+
+template <int TEAM>
+__global__ void __launch_bounds__(TEAM)
+k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st, long long B,
+     const double *__restrict__ params, const double *__restrict__ J, const double *__restrict__ bvec,
+     const uint32_t *__restrict__ mask, const double *__restrict__ lbx, const double *__restrict__ ubx,
+     const double *__restrict__ pi, const int *__restrict__ kdup, const double *__restrict__ xref,
+     int use_pen, int closest, double *__restrict__ xq, int *__restrict__ status,
+     int *__restrict__ iters) {
+  extern __shared__ double sm[];
+  QPW w;
+  w.bind(sm, S.L);
+  const int tid = threadIdx.x;
+  const int n = S.n, ms = S.m_nl;
+  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int j = tid; j < n; j += TEAM) {
+      w.lb[j] = lbx ? lbx[b * n + j] : -INFINITY;
+      w.ub[j] = ubx ? ubx[b * n + j] : INFINITY;
+      w.xs[j] = xref ? xref[b * n + j] : 0.0;
+    }
+    if (use_pen)
+      for (int i = tid; i < ms; i += TEAM) {
+        w.bb[i] = bvec[b * ms + i];
+        w.msk[i] = mask ? mask[b * ms + i] : 0xffffffffu;
+      }
+    Team<TEAM>::sync();
+    QPArgs a;
+    a.prm = params + b * S.stride;
+    a.Jg = use_pen ? J + b * S.jnnz : nullptr;
+    a.pi = pi ? pi[b] : 0.0;
+    a.kd = kdup ? (double)kdup[b] : 1.0;
+    a.use_pen = use_pen;
+    a.closest = closest;
+    QPSolver<TEAM> qp(S, st, w, a);
+    QPResult r = qp.solve();
+    const int nq = use_pen ? S.n_q : n;
+    for (int j = tid; j < n; j += TEAM) xq[b * nq + j] = w.x[j];
+    if (use_pen) {
+      int so = n;
+      for (int bi = 0; bi < S.n_blocks; bi++) {
+        const DevBlock &Bk = S.blocks[bi];
+        for (int r2 = tid; r2 < Bk.m; r2 += TEAM) {
+          xq[b * nq + so + r2] = w.s[Bk.row0 + r2];
+          if (Bk.cnt_type) xq[b * nq + so + Bk.m + r2] = w.s[ms + Bk.row0 + r2];
+        }
+        so += Bk.m * (Bk.cnt_type ? 2 : 1);
+      }
+    }
+    if (tid == 0) {
+      status[b] = r.status;
+      iters[b] = r.iters;
+    }
+    Team<TEAM>::sync();
+  }
+}
+
+template <int TEAM>
+__global__ void __launch_bounds__(TEAM)
+k_merit(const __grid_constant__ DevStruct S, long long B, const double *__restrict__ params,
+        const double *__restrict__ x, const double *__restrict__ J, const double *__restrict__ bvec,
+        const double *__restrict__ mu, double *__restrict__ merit, double *__restrict__ model,
+        double *__restrict__ max_vio, double *__restrict__ gv, double *__restrict__ gm) {
+  extern __shared__ double sm[];
+  QPW w;
+  w.bind(sm, S.L);
+  double *xc = sm + S.L.total;
+  const int tid = threadIdx.x;
+  DevSettings st;
+  memset(&st, 0, sizeof(st));
+  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+    const double *prm = params + b * S.stride;
+    SqpSolver<TEAM> sq(S, st, w, prm, xc, const_cast<double *>(J ? J + b * S.jnnz : nullptr));
+    for (int j = tid; j < S.n; j += TEAM) xc[j] = x[b * S.n + j];
+    if (bvec)
+      for (int i = tid; i < S.m_nl; i += TEAM) w.bb[i] = bvec[b * S.m_nl + i];
+    Team<TEAM>::sync();
+    eval_blocks<TEAM>(S, prm, xc, w.fv, nullptr, w.stage);
+    double vs[2 + SCO_DEV_MAX_GROUPS], msum[2 + SCO_DEV_MAX_GROUPS];
+    sq.violation_sums(vs);
+    const double ov = sq.objective();
+    const double m = mu ? mu[b] : 1.0;
+    if (J && bvec) sq.model_sums(msum);
+    if (tid == 0) {
+      if (merit) merit[b] = ov + m * vs[0];
+      if (max_vio) max_vio[b] = vs[1];
+      if (model && J && bvec) model[b] = ov + m * msum[0];
+      for (int g = 0; g < S.n_groups; g++) {
+        if (gv) gv[b * S.n_groups + g] = vs[2 + g];
+        if (gm && J && bvec) gm[b * S.n_groups + g] = msum[2 + g];
+      }
+    }
+    Team<TEAM>::sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------ handle
+struct sco_handle {
+  int device = 0;
+  int team = 32;
+  int sm_count = 0;
+  int occupancy = 1;
+  size_t smem_bytes = 0;
+  DevStruct S;
+  std::vector<void *> dev_allocs;
+  double *Jscr = nullptr;
+  size_t Jscr_ctas = 0;
+  unsigned long long *counter = nullptr;
+  // host-entry staging buffers (grow-only)
+  double *d_params = nullptr, *d_x0 = nullptr, *d_x = nullptr, *d_merit = nullptr, *d_obj = nullptr,
+         *d_vio = nullptr;
+  int *d_verdict = nullptr, *d_stats = nullptr;
+  long long cap_B = 0;
+};
+
+template <typename T>
+static int upload(sco_handle *h, const std::vector<T> &v, const T **out) {
+  T *d = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  h->dev_allocs.push_back(d);
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
+static DevField cvt(const sco_field &f) {
+  DevField d;
+  d.off = f.off;
+  d.shared = f.shared;
+  d.pad_ = 0;
+  return d;
+}
+
+static void build_layout(DevStruct &S, int team) {
+  Layout &L = S.L;
+  int off = 0;
+  auto take = [&](int cnt) {
+    int o = off;
+    off += (cnt + 1) & ~1;
+    return o;
+  };
+  const int n = S.n, ml = S.m_lin, mp = S.m_nl, sl = S.nsl * S.m_nl;
+  L.Js = take(S.sjnnz); L.S = take(n * n); L.Als = take(S.nnz_lin);
+  L.x = take(n); L.xt = take(n); L.xt2 = take(n); L.qh = take(n); L.D = take(n); L.bx = take(n);
+  L.rb = take(n); L.lb = take(n); L.ub = take(n); L.zb = take(n); L.yb = take(n); L.Eb = take(n);
+  L.dxv = take(n); L.dyb = take(n); L.xs = take(n);
+  L.El = take(ml); L.rl = take(ml); L.ll = take(ml); L.ul = take(ml); L.zl = take(ml); L.yl = take(ml);
+  L.wl = take(ml); L.dyl = take(ml);
+  L.Ep = take(mp); L.rp = take(mp); L.lp = take(mp); L.up = take(mp); L.zp = take(mp); L.yp = take(mp);
+  L.wp = take(mp); L.bb = take(mp); L.fv = take(mp); L.dyp = take(mp);
+  L.s = take(sl); L.Ds = take(sl); L.sl = take(sl); L.bs = take(sl); L.zs = take(sl); L.ys = take(sl);
+  L.Es = take(sl); L.gs = take(sl); L.hs = take(sl); L.rs = take(sl); L.dss = take(sl); L.dys = take(sl);
+  L.Minv = take(3 * mp);
+  L.red = take(8 * 16);
+  L.msk = take((mp + 1) / 2);
+  L.stage = take(std::max((team / 32) * S.stage_per_warp, 100));
+  L.total = off;
+}
+
+template <int TEAM>
+static int configure(sco_handle *h) {
+  const size_t bytes = h->smem_bytes;
+  CUDA_TRY(cudaFuncSetAttribute(k_solve<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_convexify<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_qp<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(cudaFuncSetAttribute(k_merit<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve<TEAM>, TEAM, bytes));
+  h->occupancy = std::max(occ, 1);
+  return 0;
+}
+
+extern "C" void sco_default_settings(sco_settings *s) {
+  memset(s, 0, sizeof(*s));
+  s->improve_ratio_threshold = 0.25;  // solver.py:17-28
+  s->min_trust_region_size = 1e-4;
+  s->min_approx_improve = 1e-8;
+  s->trust_shrink_ratio = 0.1;
+  s->trust_expand_ratio = 1.5;
+  s->cnt_tolerance = 1e-4;
+  s->merit_coeff_increase_ratio = 10.0;
+  s->initial_trust_region_size = 1.0;
+  s->initial_penalty_coeff = 1e3;
+  s->max_merit_coeff_increases = 1;
+  s->max_sqp_iters = 100000;
+  s->osqp_eps_abs = 1e-6;  // osqp_utils.py:10-15
+  s->osqp_eps_rel = 1e-9;
+  s->osqp_rho = 0.1;
+  s->osqp_sigma = 5e-10;
+  s->osqp_alpha = 1.6;  // OSQP defaults, SURVEY.md Appendix B
+  s->osqp_eps_prim_inf = 1e-4;
+  s->osqp_eps_dual_inf = 1e-4;
+  s->osqp_max_iter = 100000;
+  s->osqp_scaling = 10;
+  s->osqp_check_termination = 25;
+  s->osqp_adaptive_rho = 0;
+  s->osqp_adaptive_rho_interval = 0;
+  s->compound_penalty = 1;
+  s->freeze_sparsity = 1;
+  s->duplicate_rows = 1;
+  s->threads_per_problem = 0;
+}
+
+static DevSettings to_dev(const sco_settings *s) {
+  DevSettings d;
+  d.improve_ratio_threshold = s->improve_ratio_threshold;
+  d.min_trust_region_size = s->min_trust_region_size;
+  d.min_approx_improve = s->min_approx_improve;
+  d.trust_shrink_ratio = s->trust_shrink_ratio;
+  d.trust_expand_ratio = s->trust_expand_ratio;
+  d.cnt_tolerance = s->cnt_tolerance;
+  d.merit_coeff_increase_ratio = s->merit_coeff_increase_ratio;
+  d.initial_trust_region_size = s->initial_trust_region_size;
+  d.initial_penalty_coeff = s->initial_penalty_coeff;
+  d.max_merit_coeff_increases = s->max_merit_coeff_increases;
+  d.max_sqp_iters = s->max_sqp_iters;
+  d.eps_abs = s->osqp_eps_abs;
+  d.eps_rel = s->osqp_eps_rel;
+  d.rho = s->osqp_rho;
+  d.sigma = s->osqp_sigma;
+  d.alpha = s->osqp_alpha;
+  d.eps_prim_inf = s->osqp_eps_prim_inf;
+  d.eps_dual_inf = s->osqp_eps_dual_inf;
+  d.max_iter = s->osqp_max_iter;
+  d.scaling = s->osqp_scaling;
+  d.check_termination = s->osqp_check_termination;
+  d.adaptive_rho = s->osqp_adaptive_rho;
+  d.adaptive_rho_interval = s->osqp_adaptive_rho_interval;
+  d.compound_penalty = s->compound_penalty;
+  d.freeze_sparsity = s->freeze_sparsity;
+  d.duplicate_rows = s->duplicate_rows;
+  return d;
+}
+
+extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle **out) {
+  if (!desc || !out) return fail(SCO_ERR_ARG, "null argument");
+  if (desc->n <= 0 || desc->n_blocks < 0 || desc->n_blocks > SCO_MAX_BLOCKS)
+    return fail(SCO_ERR_ARG, "bad n / n_blocks");
+  if (desc->n_groups < 1 || desc->n_groups > SCO_MAX_GROUPS) return fail(SCO_ERR_ARG, "bad n_groups");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SCO_ERR_CUDA, "no CUDA device: the engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SCO_ERR_ARG, "device %d out of range", device);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(SCO_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+
+  sco_handle *h = new sco_handle();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  DevStruct &S = h->S;
+  memset(&S, 0, sizeof(S));
+  const int n = desc->n;
+  S.n = n;
+  S.m_lin = desc->m_lin;
+  S.n_blocks = desc->n_blocks;
+  S.n_groups = desc->n_groups;
+  S.stride = desc->stride;
+  S.Q = cvt(desc->Q); S.q = cvt(desc->q); S.c = cvt(desc->c);
+  S.lin_l = cvt(desc->lin_l); S.lin_u = cvt(desc->lin_u);
+  for (int g = 0; g < desc->n_groups; g++) {
+    int bits = 0;
+    if (desc->group_overlap)
+      for (int g2 = 0; g2 < desc->n_groups; g2++)
+        if (desc->group_overlap[g * desc->n_groups + g2]) bits |= 1 << g2;
+    S.overlap[g] = bits;
+  }
+  // ---- penalty rows
+  std::vector<int> row_goff, row_soff, row_w, row_eq, row_gmask, jcol;
+  int m_nl = 0, jnnz = 0, sj = 0, n_slack = 0, any_eq = 0, max_stage = 0;
+  for (int bi = 0; bi < desc->n_blocks; bi++) {
+    const sco_block_desc &b = desc->blocks[bi];
+    DevBlock &d = S.blocks[bi];
+    d.family = b.family; d.cnt_type = b.cnt_type; d.m = b.m; d.group_mask = b.group_mask;
+    d.row0 = m_nl; d.joff = jnnz;
+    memcpy(d.ipar, b.ipar, sizeof(d.ipar));
+    d.par = cvt(b.par); d.val = cvt(b.val);
+    int jw = 0;
+    if (b.family == SCO_FAM_QUADFORM) { jw = n; max_stage = std::max(max_stage, n * (n + 1) / 2); }
+    else if (b.family == SCO_FAM_CIRCLE2D) {
+      jw = 2;
+      if (b.ipar[0] * b.ipar[1] != b.m || 2 * b.ipar[0] > n) { delete h; return fail(SCO_ERR_ARG, "CIRCLE2D: m != T*K or 2T > n"); }
+    } else if (b.family == SCO_FAM_FK7) {
+      jw = 7;
+      if (b.m != 3 || n < 7) { delete h; return fail(SCO_ERR_ARG, "FK7: m must be 3 and n >= 7"); }
+    } else { delete h; return fail(SCO_ERR_UNSUPPORTED, "unknown constraint family %d", b.family); }
+    if (jw > 32) { delete h; return fail(SCO_ERR_UNSUPPORTED, "Jacobian rows wider than 32 entries are not supported (n=%d)", n); }
+    d.jw = jw;
+    const int ldj = (jw % 2 == 0) ? jw + 1 : jw;
+    for (int r = 0; r < b.m; r++) {
+      row_goff.push_back(jnnz + r * jw);
+      row_soff.push_back(sj + r * ldj);
+      row_w.push_back(jw);
+      row_eq.push_back(b.cnt_type == SCO_CNT_EQ ? 1 : 0);
+      row_gmask.push_back(b.group_mask);
+      for (int k = 0; k < jw; k++) {
+        int col = 0;
+        if (b.family == SCO_FAM_QUADFORM) col = k;
+        else if (b.family == SCO_FAM_CIRCLE2D) col = 2 * (r / b.ipar[1]) + k;
+        else col = n - 7 + k;
+        jcol.push_back(col);
+      }
+    }
+    if (b.cnt_type == SCO_CNT_EQ) any_eq = 1;
+    n_slack += b.m * (b.cnt_type == SCO_CNT_EQ ? 2 : 1);
+    m_nl += b.m;
+    jnnz += b.m * jw;
+    sj += b.m * ldj;
+  }
+  S.m_nl = m_nl; S.jnnz = jnnz; S.sjnnz = sj; S.n_slack = n_slack; S.n_q = n + n_slack;
+  S.nsl = any_eq ? 2 : 1;
+  S.stage_per_warp = (max_stage + 1) & ~1;
+  // CSC over user variables of the stored Jacobian pattern
+  std::vector<int> pc_ptr(n + 1, 0), pc_e, pc_r;
+  {
+    std::vector<std::vector<std::pair<int, int>>> cols(n);
+    for (int i = 0; i < m_nl; i++)
+      for (int k = 0; k < row_w[i]; k++) cols[jcol[row_goff[i] + k]].push_back({row_soff[i] + k, i});
+    for (int j = 0; j < n; j++) {
+      pc_ptr[j + 1] = pc_ptr[j] + (int)cols[j].size();
+      for (auto &pr : cols[j]) { pc_e.push_back(pr.first); pc_r.push_back(pr.second); }
+    }
+  }
+  // linear rows
+  std::vector<int> lrp(desc->m_lin + 1, 0), lcol, lcptr(n + 1, 0), lcentry, lcrow;
+  std::vector<double> lval;
+  if (desc->m_lin > 0) {
+    if (!desc->lin_rowptr || !desc->lin_col || !desc->lin_val) { delete h; return fail(SCO_ERR_ARG, "m_lin > 0 but CSR arrays are null"); }
+    lrp.assign(desc->lin_rowptr, desc->lin_rowptr + desc->m_lin + 1);
+    const int nnz = lrp[desc->m_lin];
+    lcol.assign(desc->lin_col, desc->lin_col + nnz);
+    lval.assign(desc->lin_val, desc->lin_val + nnz);
+    std::vector<std::vector<std::pair<int, int>>> cols(n);
+    for (int r = 0; r < desc->m_lin; r++)
+      for (int p = lrp[r]; p < lrp[r + 1]; p++) {
+        if (lcol[p] < 0 || lcol[p] >= n) { delete h; return fail(SCO_ERR_ARG, "linear row column out of range"); }
+        cols[lcol[p]].push_back({p, r});
+      }
+    for (int j = 0; j < n; j++) {
+      lcptr[j + 1] = lcptr[j] + (int)cols[j].size();
+      for (auto &pr : cols[j]) { lcentry.push_back(pr.first); lcrow.push_back(pr.second); }
+    }
+    S.nnz_lin = nnz;
+  }
+  std::vector<double> shared_v;
+  if (desc->shared_len > 0 && desc->shared) shared_v.assign(desc->shared, desc->shared + desc->shared_len);
+  int rc = 0;
+  rc |= upload(h, row_goff, &S.row_goff); rc |= upload(h, row_soff, &S.row_soff);
+  rc |= upload(h, row_w, &S.row_w); rc |= upload(h, row_eq, &S.row_eq);
+  rc |= upload(h, row_gmask, &S.row_gmask); rc |= upload(h, jcol, &S.jcol_g);
+  rc |= upload(h, pc_ptr, &S.pc_ptr); rc |= upload(h, pc_e, &S.pc_e); rc |= upload(h, pc_r, &S.pc_r);
+  rc |= upload(h, lrp, &S.lin_rowptr); rc |= upload(h, lcol, &S.lin_col); rc |= upload(h, lval, &S.lin_val);
+  rc |= upload(h, lcptr, &S.lin_cptr); rc |= upload(h, lcentry, &S.lin_centry); rc |= upload(h, lcrow, &S.lin_crow);
+  rc |= upload(h, shared_v, &S.shared);
+  if (rc) { sco_destroy(h); return SCO_ERR_CUDA; }
+  // ---- team size and shared-memory layout
+  const int work = std::max(std::max(n, m_nl), desc->m_lin);
+  int team = work <= 40 ? 32 : work <= 96 ? 64 : work <= 192 ? 128 : 256;
+  for (;;) {
+    build_layout(S, team);
+    h->smem_bytes = (size_t)(S.L.total + ((n + 1) & ~1)) * sizeof(double);
+    if (h->smem_bytes <= (size_t)prop.sharedMemPerBlockOptin) break;
+    sco_destroy(h);
+    return fail(SCO_ERR_UNSUPPORTED, "problem working set (%zu B) exceeds shared memory per block (%zu B)",
+                h->smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
+  }
+  h->team = team;
+  int crc = team == 32 ? configure<32>(h) : team == 64 ? configure<64>(h) : team == 128 ? configure<128>(h) : configure<256>(h);
+  if (crc) { sco_destroy(h); return crc; }
+  h->Jscr_ctas = (size_t)h->sm_count * h->occupancy;
+  if (cudaMalloc(&h->Jscr, std::max<size_t>(h->Jscr_ctas * std::max(jnnz, 1), 1) * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->counter, sizeof(unsigned long long)) != cudaSuccess) {
+    sco_destroy(h);
+    return fail(SCO_ERR_CUDA, "cudaMalloc of scratch failed");
+  }
+  *out = h;
+  return SCO_OK;
+}
+
+extern "C" int sco_destroy(sco_handle *h) {
+  if (!h) return SCO_OK;
+  cudaSetDevice(h->device);
+  for (void *p : h->dev_allocs) cudaFree(p);
+  cudaFree(h->Jscr); cudaFree(h->counter);
+  cudaFree(h->d_params); cudaFree(h->d_x0); cudaFree(h->d_x); cudaFree(h->d_merit); cudaFree(h->d_obj);
+  cudaFree(h->d_vio); cudaFree(h->d_verdict); cudaFree(h->d_stats);
+  delete h;
+  return SCO_OK;
+}
+
+extern "C" int sco_query(sco_handle *h, int64_t *out8) {
+  if (!h || !out8) return fail(SCO_ERR_ARG, "null argument");
+  out8[0] = h->S.n; out8[1] = h->S.m_nl; out8[2] = h->S.n_slack; out8[3] = h->S.jnnz;
+  out8[4] = h->S.n_q; out8[5] = (int64_t)h->smem_bytes; out8[6] = h->team; out8[7] = h->occupancy;
+  return SCO_OK;
+}
+
+#define DISPATCH(KERNEL, GRID, STREAM, ...)                                                        \
+  do {                                                                                             \
+    switch (h->team) {                                                                             \
+      case 32: KERNEL<32><<<GRID, 32, h->smem_bytes, STREAM>>>(__VA_ARGS__); break;                \
+      case 64: KERNEL<64><<<GRID, 64, h->smem_bytes, STREAM>>>(__VA_ARGS__); break;                \
+      case 128: KERNEL<128><<<GRID, 128, h->smem_bytes, STREAM>>>(__VA_ARGS__); break;             \
+      default: KERNEL<256><<<GRID, 256, h->smem_bytes, STREAM>>>(__VA_ARGS__); break;              \
+    }                                                                                              \
+  } while (0)
+
+extern "C" int sco_solve_batch(sco_handle *h, int64_t B, const double *d_params, const double *d_x0,
+                               const sco_settings *s, double *d_x_out, int32_t *d_verdict,
+                               double *d_merit, double *d_objective, double *d_max_vio,
+                               int32_t *d_stats, void *stream) {
+  if (!h || !s || !d_params || !d_x0 || !d_x_out || !d_verdict) return fail(SCO_ERR_ARG, "null argument");
+  if (B <= 0) return SCO_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DevSettings d = to_dev(s);
+  CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+  const long long grid = std::min<long long>(B, (long long)h->Jscr_ctas);
+  DISPATCH(k_solve, (unsigned)grid, st, h->S, d, (long long)B, d_params, d_x0, d_x_out, d_verdict, d_merit,
+           d_objective, d_max_vio, d_stats, h->Jscr, h->counter);
+  CUDA_TRY(cudaGetLastError());
+  return SCO_OK;
+}
+
+template <typename T>
+static int grow(T **p, size_t count) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  CUDA_TRY(cudaMalloc(p, std::max<size_t>(count, 1) * sizeof(T)));
+  return 0;
+}
+
+extern "C" int sco_solve_batch_host(sco_handle *h, int64_t B, const double *params, const double *x0,
+                                    const sco_settings *s, double *x_out, int32_t *verdict,
+                                    double *merit, double *objective, double *max_vio,
+                                    int32_t *stats) {
+  if (!h || !s || !params || !x0 || !x_out || !verdict) return fail(SCO_ERR_ARG, "null argument");
+  if (B <= 0) return SCO_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int n = h->S.n;
+  if (B > h->cap_B) {
+    int rc = 0;
+    rc |= grow(&h->d_params, (size_t)B * h->S.stride); rc |= grow(&h->d_x0, (size_t)B * n);
+    rc |= grow(&h->d_x, (size_t)B * n); rc |= grow(&h->d_merit, (size_t)B); rc |= grow(&h->d_obj, (size_t)B);
+    rc |= grow(&h->d_vio, (size_t)B); rc |= grow(&h->d_verdict, (size_t)B); rc |= grow(&h->d_stats, (size_t)4 * B);
+    if (rc) return SCO_ERR_CUDA;
+    h->cap_B = B;
+  }
+  cudaStream_t st = 0;
+  CUDA_TRY(cudaMemcpyAsync(h->d_params, params, (size_t)B * h->S.stride * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_x0, x0, (size_t)B * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = sco_solve_batch(h, B, h->d_params, h->d_x0, s, h->d_x, h->d_verdict, h->d_merit, h->d_obj,
+                           h->d_vio, h->d_stats, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(x_out, h->d_x, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(verdict, h->d_verdict, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (merit) CUDA_TRY(cudaMemcpyAsync(merit, h->d_merit, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (objective) CUDA_TRY(cudaMemcpyAsync(objective, h->d_obj, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (max_vio) CUDA_TRY(cudaMemcpyAsync(max_vio, h->d_vio, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (stats) CUDA_TRY(cudaMemcpyAsync(stats, h->d_stats, (size_t)4 * B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return SCO_OK;
+}
+
+static unsigned stage_grid(sco_handle *h, int64_t B) {
+  return (unsigned)std::min<long long>(B, (long long)h->Jscr_ctas);
+}
+
+extern "C" int sco_convexify(sco_handle *h, int64_t B, const double *d_params, const double *d_x,
+                             double *d_f, double *d_J, double *d_b, double *d_obj, void *stream) {
+  if (!h || !d_params || !d_x) return fail(SCO_ERR_ARG, "null argument");
+  if (B <= 0) return SCO_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(k_convexify, stage_grid(h, B), st, h->S, (long long)B, d_params, d_x, d_f, d_J, d_b, d_obj, h->Jscr);
+  CUDA_TRY(cudaGetLastError());
+  return SCO_OK;
+}
+
+extern "C" int sco_qp_solve(sco_handle *h, int64_t B, const double *d_params, const double *d_J,
+                            const double *d_b, const uint32_t *d_mask, const double *d_lbx,
+                            const double *d_ubx, const double *d_pi, const int32_t *d_kdup,
+                            const double *d_xref, int use_penalty, int closest_point,
+                            const sco_settings *s, double *d_xq, int32_t *d_status, int32_t *d_iters,
+                            void *stream) {
+  if (!h || !s || !d_params || !d_xq || !d_status || !d_iters) return fail(SCO_ERR_ARG, "null argument");
+  if (use_penalty && h->S.m_nl > 0 && (!d_J || !d_b)) return fail(SCO_ERR_ARG, "penalty rows need J and b");
+  if (closest_point && !d_xref) return fail(SCO_ERR_ARG, "closest_point needs xref");
+  if (B <= 0) return SCO_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DevSettings d = to_dev(s);
+  DISPATCH(k_qp, stage_grid(h, B), st, h->S, d, (long long)B, d_params, d_J, d_b, d_mask, d_lbx, d_ubx, d_pi,
+           d_kdup, d_xref, use_penalty, closest_point, d_xq, d_status, d_iters);
+  CUDA_TRY(cudaGetLastError());
+  return SCO_OK;
+}
+
+extern "C" int sco_merit(sco_handle *h, int64_t B, const double *d_params, const double *d_x,
+                         const double *d_J, const double *d_b, const double *d_mu, double *d_merit,
+                         double *d_model, double *d_max_vio, double *d_gv, double *d_gm, void *stream) {
+  if (!h || !d_params || !d_x) return fail(SCO_ERR_ARG, "null argument");
+  if (B <= 0) return SCO_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(k_merit, stage_grid(h, B), st, h->S, (long long)B, d_params, d_x, d_J, d_b, d_mu, d_merit, d_model,
+           d_max_vio, d_gv, d_gm);
+  CUDA_TRY(cudaGetLastError());
+  return SCO_OK;
+}

@@ -1,0 +1,141 @@
+// sco_families.cuh -- batched expression evaluation and convexification on device.
+//
+// Replaces Expr.eval / Expr.grad / Expr._num_grad (sco_py/expr.py:34-41,61-69,78-100) for the
+// closed constraint families the engine supports, and the affine-model offset of
+// Expr.convexify degree 1 (expr.py:139-142) + Eq/LEqExpr.convexify (expr.py:327-328,366-367):
+//   J = grad f(x),  b = f(x) - J x - val.
+// A team evaluates one problem: x is in shared memory, the family parameters are streamed from
+// the problem's parameter block in HBM with coalesced loads (a warp reads 32 consecutive doubles).
+#pragma once
+#include "sco_device.cuh"
+
+#define FAM_QUADFORM 1
+#define FAM_CIRCLE2D 2
+#define FAM_FK7 3
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- QUADFORM: f_j = 0.5 x'P_j x + a_j'x, P_j packed upper row-major, one warp per row ----
+template <int TEAM>
+__device__ void eval_quadform(const DevStruct &S, const DevBlock &B, const double *par,
+                              const double *x, double *f, double *Jout, double *stage) {
+  const int n = S.n, ntri = n * (n + 1) / 2, m = B.m;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *buf = stage + warp * S.stage_per_warp;
+  const double *A = par + (size_t)m * ntri;
+  for (int j = warp; j < m; j += TEAM / 32) {
+    const double *Pj = par + (size_t)j * ntri;
+    for (int e = lane; e < ntri; e += 32) buf[e] = __ldg(Pj + e);
+    __syncwarp();
+    double fj = 0.0;
+    for (int r = lane; r < n; r += 32) {
+      double acc = 0.0;
+      for (int cc = 0; cc < r; cc++) acc += buf[cc * n - (cc * (cc - 1)) / 2 + (r - cc)] * x[cc];
+      const int base = r * n - (r * (r - 1)) / 2 - r;
+      for (int cc = r; cc < n; cc++) acc += buf[base + cc] * x[cc];
+      const double aj = __ldg(A + j * n + r);
+      if (Jout) Jout[j * n + r] = acc + aj;
+      fj += x[r] * (0.5 * acc + aj);
+    }
+    fj = warp_sum(fj);
+    if (lane == 0) f[j] = fj;
+    __syncwarp();
+  }
+}
+
+// ---- CIRCLE2D: row t*K+k: R_k - |p_t - c_k| ----
+template <int TEAM>
+__device__ void eval_circle2d(const DevStruct &S, const DevBlock &B, const double *par,
+                              const double *x, double *f, double *Jout) {
+  const int K = B.ipar[1], m = B.m;
+  for (int r = threadIdx.x; r < m; r += TEAM) {
+    const int t = r / K, k = r % K;
+    const double dx = x[2 * t] - par[2 * k], dy = x[2 * t + 1] - par[2 * k + 1];
+    const double dist = sqrt(dx * dx + dy * dy);
+    f[r] = par[2 * K + k] - dist;
+    if (Jout) {
+      Jout[2 * r] = -dx / dist;
+      Jout[2 * r + 1] = -dy / dist;
+    }
+  }
+}
+
+// ---- FK7: flange position of a 7-link modified-DH chain.  tab = a[7] d[7] cos(alpha)[7]
+// sin(alpha)[7] flange base_step ----
+__device__ __forceinline__ void fk7_pos(const double *q, const double *tab, double out[3]) {
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double p[3] = {0, 0, 0};
+  for (int i = 0; i < 7; i++) {
+    const double ai = tab[i], di = tab[7 + i], ca = tab[14 + i], sa = tab[21 + i];
+    double st, ct;
+    sincos(q[i], &st, &ct);
+    const double Ri[9] = {ct, -st, 0.0, st * ca, ct * ca, -sa, st * sa, ct * sa, ca};
+    const double pi3[3] = {ai, -sa * di, ca * di};
+    for (int r = 0; r < 3; r++) p[r] = p[r] + (R[3 * r] * pi3[0] + R[3 * r + 1] * pi3[1] + R[3 * r + 2] * pi3[2]);
+    double Rn[9];
+    for (int r = 0; r < 3; r++)
+      for (int cc = 0; cc < 3; cc++)
+        Rn[3 * r + cc] = R[3 * r] * Ri[cc] + R[3 * r + 1] * Ri[3 + cc] + R[3 * r + 2] * Ri[6 + cc];
+    for (int e = 0; e < 9; e++) R[e] = Rn[e];
+  }
+  const double fl = tab[28];
+  for (int r = 0; r < 3; r++) out[r] = p[r] + (R[3 * r] * 0.0 + R[3 * r + 1] * 0.0 + R[3 * r + 2] * fl);
+}
+
+// Central differences at steps h and 2h, Richardson-combined -- the scheme of
+// oracle/shims/numdifftools (restating numdifftools.Jacobian as called at expr.py:67).
+template <int TEAM>
+__device__ void eval_fk7(const DevStruct &S, const DevBlock &B, const double *tab, const double *x,
+                         double *f, double *Jout, double *stage) {
+  const int n = S.n, t = threadIdx.x;
+  const double *q = x + (n - 7);
+  if (t == 0) {
+    double o[3];
+    fk7_pos(q, tab, o);
+    f[0] = o[0]; f[1] = o[1]; f[2] = o[2];
+  }
+  if (Jout) {
+    // thread e = col*4 + (mult_idx*2 + sign): 28 evaluations -> stage[e*3 .. e*3+2]; stage[84+..] = hh
+    for (int e = t; e < 28; e += TEAM) {
+      const int col = e >> 2, mi = (e >> 1) & 1, sg = e & 1;
+      double qq[7];
+      for (int k = 0; k < 7; k++) qq[k] = q[k];
+      const double h0 = tab[29] * fmax(log1p(fabs(q[col])), 1.0);
+      const double h = h0 * (mi ? 2.0 : 1.0);
+      const double xp = q[col] + h, xm = q[col] - h;
+      qq[col] = sg ? xm : xp;
+      double o[3];
+      fk7_pos(qq, tab, o);
+      stage[e * 3] = o[0]; stage[e * 3 + 1] = o[1]; stage[e * 3 + 2] = o[2];
+      if (sg == 0) stage[84 + col * 2 + mi] = xp - xm;
+    }
+    Team<TEAM>::sync();
+    for (int e = t; e < 21; e += TEAM) {
+      const int r = e / 7, col = e % 7;
+      const double d1 = (stage[(col * 4 + 0) * 3 + r] - stage[(col * 4 + 1) * 3 + r]) / stage[84 + col * 2];
+      const double d2 = (stage[(col * 4 + 2) * 3 + r] - stage[(col * 4 + 3) * 3 + r]) / stage[84 + col * 2 + 1];
+      Jout[r * 7 + col] = (4.0 * d1 - d2) / 3.0;
+    }
+  }
+}
+
+// Evaluate every block at x: fv[row] = f_row(x); if Jg != null also the stored Jacobian entries.
+// Ends with a team sync.
+template <int TEAM>
+__device__ void eval_blocks(const DevStruct &S, const double *prm, const double *x, double *fv,
+                            double *Jg, double *stage) {
+  for (int bi = 0; bi < S.n_blocks; bi++) {
+    const DevBlock &B = S.blocks[bi];
+    const double *par = field_ptr(S, B.par, prm);
+    double *f = fv + B.row0;
+    double *J = Jg ? Jg + B.joff : nullptr;
+    if (B.family == FAM_QUADFORM) eval_quadform<TEAM>(S, B, par, x, f, J, stage);
+    else if (B.family == FAM_CIRCLE2D) eval_circle2d<TEAM>(S, B, par, x, f, J);
+    else if (B.family == FAM_FK7) eval_fk7<TEAM>(S, B, par, x, f, J, stage);
+  }
+  Team<TEAM>::sync();
+}

@@ -1,0 +1,251 @@
+// sco_sqp.cuh -- per-problem penalty-SQP state machine, run by the team that owns the problem.
+//
+// Replaces Solver._penalty_sqp / _min_merit_fn and its predicates
+// (sco_py/sco_osqp/solver.py:62-283), Prob.find_closest_feasible_point (prob.py:369-412),
+// Prob.update_obj's penalty bookkeeping (prob.py:414-426, quirks C-1..C-3 of SURVEY.md
+// Appendix C), Prob.get_value / get_approx_value / get_max_cnt_violation (prob.py:547-630),
+// Prob.add_trust_region / save / restore (prob.py:514-519,639-652; variable.py:37-73).
+// Every scalar decision is taken on team-uniform values, so control flow never diverges
+// inside a team; different problems (teams) follow different paths freely.
+#pragma once
+#include "sco_device.cuh"
+#include "sco_families.cuh"
+#include "sco_qp.cuh"
+
+struct SqpOut {
+  int verdict;
+  double merit, objective, max_vio;
+  int sqp_iters, qp_solves, admm_iters, last_status;
+};
+
+template <int TEAM>
+struct SqpSolver {
+  const DevStruct &S;
+  const DevSettings &st;
+  QPW &w;
+  const double *prm;
+  double *xc;   // current iterate (shared memory)
+  double *Jg;   // unscaled Jacobian entries of the last convexification (global scratch)
+  const int tid, n, m_nl, ng;
+
+  __device__ SqpSolver(const DevStruct &S_, const DevSettings &st_, QPW &w_, const double *prm_,
+                       double *xc_, double *Jg_)
+      : S(S_), st(st_), w(w_), prm(prm_), xc(xc_), Jg(Jg_), tid(threadIdx.x), n(S_.n),
+        m_nl(S_.m_nl), ng(S_.m_nl ? S_.n_groups : 0) {}
+
+  __device__ __forceinline__ void sync() { Team<TEAM>::sync(); }
+
+  // QuadExpr.eval (expr.py:205-206): 0.5 x'Qx + q'x + c at xc
+  __device__ double objective() {
+    const double *Qg = field_ptr(S, S.Q, prm), *qg = field_ptr(S, S.q, prm), *cg = field_ptr(S, S.c, prm);
+    double v[1] = {0.0};
+    for (int k = tid; k < n; k += TEAM) {
+      double acc = 0.0;
+      if (Qg)
+        for (int j = 0; j < n; j++) acc += Qg[j * n + k] * xc[j];
+      v[0] += xc[k] * (0.5 * acc + (qg ? qg[k] : 0.0));
+    }
+    Team<TEAM>::reduce_sum(v, w.red);
+    return v[0] + (cg ? cg[0] : 0.0);
+  }
+
+  // violations from w.fv (raw f at xc): out[0] = sum, out[1] = max, out[2+g] = group sums
+  __device__ void violation_sums(double *out) {
+    double v[1 + SCO_DEV_MAX_GROUPS], mx[1] = {0.0};
+    for (int k = 0; k < 1 + SCO_DEV_MAX_GROUPS; k++) v[k] = 0.0;
+    for (int bi = 0; bi < S.n_blocks; bi++) {
+      const DevBlock &B = S.blocks[bi];
+      const double *val = field_ptr(S, B.val, prm);
+      for (int r = tid; r < B.m; r += TEAM) {
+        const double d = w.fv[B.row0 + r] - (val ? val[r] : 0.0);
+        const double vio = B.cnt_type ? fabs(d) : fmax(d, 0.0);  // prob.py:582-590
+        v[0] += vio;
+        mx[0] = fmax(mx[0], vio);
+        for (int g = 0; g < ng; g++)
+          if ((B.group_mask >> g) & 1) v[1 + g] += vio;
+      }
+    }
+    Team<TEAM>::reduce_sum(v, w.red);
+    Team<TEAM>::reduce_max(mx, w.red);
+    out[0] = v[0];
+    out[1] = mx[0];
+    for (int g = 0; g < SCO_DEV_MAX_GROUPS; g++) out[2 + g] = v[1 + g];
+  }
+
+  // penalties of the affine models at xc (unmasked J, prob.py:624-630): out[0] = sum, out[2+g]
+  __device__ void model_sums(double *out) {
+    double v[1 + SCO_DEV_MAX_GROUPS];
+    for (int k = 0; k < 1 + SCO_DEV_MAX_GROUPS; k++) v[k] = 0.0;
+    for (int i = tid; i < m_nl; i += TEAM) {
+      const int go = S.row_goff[i], wd = S.row_w[i];
+      double acc = w.bb[i];
+      for (int k = 0; k < wd; k++) acc += Jg[go + k] * xc[S.jcol_g[go + k]];
+      const double pen = S.row_eq[i] ? fabs(acc) : fmax(acc, 0.0);
+      v[0] += pen;
+      const int gm = S.row_gmask[i];
+      for (int g = 0; g < ng; g++)
+        if ((gm >> g) & 1) v[1 + g] += pen;
+    }
+    Team<TEAM>::reduce_sum(v, w.red);
+    out[0] = v[0];
+    out[1] = 0.0;
+    for (int g = 0; g < SCO_DEV_MAX_GROUPS; g++) out[2 + g] = v[1 + g];
+  }
+
+  // Prob.convexify at xc: fv, Jg, bb = f - J x - val ; first call freezes the sparsity masks
+  __device__ void convexify(bool &mask_set) {
+    eval_blocks<TEAM>(S, prm, xc, w.fv, Jg, w.stage);
+    for (int bi = 0; bi < S.n_blocks; bi++) {
+      const DevBlock &B = S.blocks[bi];
+      const double *val = field_ptr(S, B.val, prm);
+      for (int r = tid; r < B.m; r += TEAM) {
+        const int i = B.row0 + r, go = S.row_goff[i], wd = S.row_w[i];
+        double acc = 0.0;
+        uint32_t mk = 0;
+        for (int k = 0; k < wd; k++) {
+          const double jv = Jg[go + k];
+          acc += jv * xc[S.jcol_g[go + k]];
+          if (jv != 0.0) mk |= (1u << k);
+        }
+        w.bb[i] = -acc + w.fv[i] - (val ? val[r] : 0.0);
+        if (!mask_set) w.msk[i] = st.freeze_sparsity ? mk : 0xffffffffu;
+      }
+    }
+    mask_set = true;
+    sync();
+  }
+
+  __device__ SqpOut run(const double *x0) {
+    SqpOut o;
+    o.verdict = 0; o.merit = 0; o.objective = 0; o.max_vio = 0;
+    o.sqp_iters = 0; o.qp_solves = 0; o.admm_iters = 0; o.last_status = 0;
+    for (int j = tid; j < n; j += TEAM) xc[j] = x0[j];
+    sync();
+    double mu = st.initial_penalty_coeff;
+    double vs[2 + SCO_DEV_MAX_GROUPS], ms_[2 + SCO_DEV_MAX_GROUPS];
+    bool finished = false;
+    // ---- find_closest_feasible_point (prob.py:369-412): default OSQP settings (solver.py:81)
+    {
+      for (int j = tid; j < n; j += TEAM) { w.xs[j] = xc[j]; w.lb[j] = -INFINITY; w.ub[j] = INFINITY; }
+      sync();
+      QPArgs a;
+      a.prm = prm; a.Jg = nullptr; a.pi = 0.0; a.kd = 0.0; a.use_pen = 0; a.closest = 1;
+      DevSettings d = st;
+      d.eps_abs = 1e-6; d.eps_rel = 1e-9; d.max_iter = 100000; d.rho = 0.1; d.sigma = 5e-10;
+      d.adaptive_rho = 0;
+      QPSolver<TEAM> qp(S, d, w, a);
+      QPResult r = qp.solve();
+      o.qp_solves++; o.admm_iters += r.iters; o.last_status = r.status;
+      if (r.status == 1 || r.status == 2) {
+        for (int j = tid; j < n; j += TEAM) xc[j] = w.x[j];
+        sync();
+      } else {
+        finished = true;  // solver.py:81-82 -> False
+      }
+    }
+    double pi = 1.0, kd = 0.0;
+    bool mask_set = false;
+    if (!finished) {
+      bool success = false;
+      int verdict = 0;
+      for (int inc = 0; inc < st.max_merit_coeff_increases && !finished; inc++) {
+        // ---------------- _min_merit_fn(prob, mu, delta0) ----------------
+        double delta = st.initial_trust_region_size;
+        bool done_mm = false;
+        success = false;
+        while (!done_mm) {
+          if (o.sqp_iters >= st.max_sqp_iters) { verdict = -1; finished = true; break; }
+          o.sqp_iters++;
+          convexify(mask_set);
+          kd = st.duplicate_rows ? kd + 1.0 : 1.0;      // prob.py:508-509
+          pi = st.compound_penalty ? pi * mu : mu;      // prob.py:424-426
+          violation_sums(vs);
+          const double merit = objective() + mu * vs[0];
+          double mvec[SCO_DEV_MAX_GROUPS];
+          for (int g = 0; g < SCO_DEV_MAX_GROUPS; g++) mvec[g] = vs[2 + g];
+          for (int j = tid; j < n; j += TEAM) w.xs[j] = xc[j];  // prob.save()
+          sync();
+          while (true) {  // trust-region loop, solver.py:136-251
+            for (int j = tid; j < n; j += TEAM) { w.lb[j] = w.xs[j] - delta; w.ub[j] = w.xs[j] + delta; }
+            sync();
+            QPArgs a;
+            a.prm = prm; a.Jg = Jg; a.pi = pi; a.kd = kd; a.use_pen = 1; a.closest = 0;
+            QPSolver<TEAM> qp(S, st, w, a);
+            QPResult r = qp.solve();
+            o.qp_solves++; o.admm_iters += r.iters; o.last_status = r.status;
+            if (r.status == 1 || r.status == 2) {  // prob.py:197-205
+              for (int j = tid; j < n; j += TEAM) xc[j] = w.x[j];
+              sync();
+            }
+            model_sums(ms_);
+            const double obj_new = objective();
+            const double model_merit = obj_new + mu * ms_[0];
+            eval_blocks<TEAM>(S, prm, xc, w.fv, nullptr, w.stage);
+            violation_sums(vs);
+            const double new_merit = obj_new + mu * vs[0];
+            double approx = merit - model_merit;
+            if (approx == 0.0) approx += 1e-12;  // solver.py:151-153
+            const double exact = merit - new_merit;
+            const double ratio = exact / approx;
+            bool restore = false, ret = false, retval = false;
+            if (approx < -1e-5) { restore = true; ret = true; retval = false; }          // _bad_model
+            else if (approx < st.min_approx_improve) { restore = true; ret = true; retval = true; }  // _y_converged
+            else {
+              bool nonconv = false;  // solver.py:209-235
+              for (int g = 0; g < ng; g++) {
+                const double av = mvec[g] - ms_[2 + g];
+                if (mvec[g] > st.cnt_tolerance && av < st.min_approx_improve) {
+                  bool ov = false;
+                  for (int g2 = 0; g2 < ng; g2++)
+                    if (g2 != g && ((S.overlap[g] >> g2) & 1) && (mvec[g2] - ms_[2 + g2]) > st.min_approx_improve)
+                      ov = true;
+                  if (!ov) nonconv = true;
+                }
+              }
+              if (nonconv) { restore = true; ret = true; retval = true; }
+            }
+            if (ret) {
+              for (int j = tid; j < n; j += TEAM) xc[j] = w.xs[j];
+              sync();
+              success = retval;
+              done_mm = true;
+              break;
+            }
+            if (exact < 0.0 || ratio < st.improve_ratio_threshold) {  // _shrink_trust_region
+              for (int j = tid; j < n; j += TEAM) xc[j] = w.xs[j];
+              sync();
+              delta *= st.trust_shrink_ratio;
+            } else {
+              delta *= st.trust_expand_ratio;
+              break;  // next SQP iteration
+            }
+            if (delta < st.min_trust_region_size) {  // _x_converged
+              success = true;
+              done_mm = true;
+              break;
+            }
+            (void)restore;
+          }
+        }
+        if (finished) break;
+        // ---------------- solver.py:94-101 ----------------
+        eval_blocks<TEAM>(S, prm, xc, w.fv, nullptr, w.stage);
+        violation_sums(vs);
+        if (vs[1] > st.cnt_tolerance) {
+          if (inc + 1 < st.max_merit_coeff_increases) mu *= st.merit_coeff_increase_ratio;
+        } else {
+          verdict = success ? 1 : 0;
+          finished = true;
+        }
+      }
+      o.verdict = verdict;  // falling out of the loop: solver.py:105 -> False
+    }
+    // final report at xc with the last penalty coefficient used
+    eval_blocks<TEAM>(S, prm, xc, w.fv, nullptr, w.stage);
+    violation_sums(vs);
+    o.objective = objective();
+    o.merit = o.objective + mu * vs[0];
+    o.max_vio = vs[1];
+    return o;
+  }
+};

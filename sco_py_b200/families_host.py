@@ -13,9 +13,13 @@ FK7_ALPHA = np.array([0.0, -np.pi / 2, np.pi / 2, np.pi / 2, -np.pi / 2, np.pi /
 FK7_FLANGE = 0.107
 
 
+FD_BASE_STEP = np.finfo(float).eps ** (1.0 / 2.5)  # numdifftools default for first derivatives
+
+
 def fk7_table():
-    """28 doubles handed to the kernels: a[7], d[7], cos(alpha)[7], sin(alpha)[7]."""
-    return np.concatenate([FK7_A, FK7_D, np.cos(FK7_ALPHA), np.sin(FK7_ALPHA)])
+    """30 doubles handed to the kernels: a[7], d[7], cos(alpha)[7], sin(alpha)[7], flange, FD base step."""
+    return np.concatenate([FK7_A, FK7_D, np.cos(FK7_ALPHA), np.sin(FK7_ALPHA),
+                           [FK7_FLANGE, FD_BASE_STEP]])
 
 
 def fk7_pos(qj):

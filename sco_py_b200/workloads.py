@@ -134,8 +134,9 @@ JOINT_LIMIT = 2.9
 
 
 def arm_structure(T=20):
+    from .families_host import fk7_table
     n = 7 * T
-    Qs = smoothness_Q(T, 7).ravel()
+    Qs = np.concatenate([smoothness_Q(T, 7).ravel(), fk7_table()])
     # joint limits: x <= 2.9 and -x <= 2.9 (two LEqExpr(AffExpr(+-I))), then the start pin
     A = np.vstack([np.eye(n), -np.eye(n), np.eye(7, n)])
     rp, ci, cv = _csr(A)
@@ -145,7 +146,7 @@ def arm_structure(T=20):
     lin_l = Field(off, False); off += m_lin
     lin_u = Field(off, False); off += m_lin
     val = Field(off, False); off += 3
-    blk = Block(FAM_FK7, CNT_EQ, 3, Field(-1, False), val, ipar=[T, 0, 0, 0, 0, 0, 0, 0], jw=7)
+    blk = Block(FAM_FK7, CNT_EQ, 3, Field(n * n, True), val, ipar=[T, 0, 0, 0, 0, 0, 0, 0], jw=7)
     return Structure(n=n, stride=off, Q=Field(0, True), q=Field(-1, False), c=Field(-1, False),
                      m_lin=m_lin, lin_rowptr=rp, lin_col=ci, lin_val=cv, lin_l=lin_l, lin_u=lin_u,
                      blocks=[blk], shared=Qs)

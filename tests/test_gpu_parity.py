@@ -1,0 +1,119 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances (float64 path, BASELINE.json north_star: 1e-4 relative on the solution, 1e-5 absolute
+on violation, same verdict):
+  * expression values / Jacobians / affine offsets: 1e-9 (analytic), 1e-7 (finite-difference FK)
+  * one QP (same scaling, same ADMM iteration, different linear algebra): |dx| <= 1e-7 * max(1,|x|),
+    identical status, identical iteration count
+  * full penalty-SQP solve: identical verdict, |dx| <= 1e-4 * max(1,|x|), |d max_vio| <= 1e-5
+"""
+import numpy as np
+import pytest
+
+import helpers
+import sqp_port
+from sco_py_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [("qcqp", 6), ("point_robot", 3), ("arm", 3)]
+
+
+@pytest.fixture(scope="module")
+def engines():
+    import torch
+    from sco_py_b200.engine import Engine
+    assert torch.cuda.is_available()
+    out = {}
+    for name, B in CONFIGS:
+        st, params, x0 = W.GENERATORS[name](B)
+        out[name] = (Engine(st), st, params, x0)
+    yield out
+    for e in out.values():
+        e[0].close()
+
+
+def _settings(**kw):
+    from sco_py_b200.engine import make_settings
+    return make_settings(solver=W.SOLVER_SETTINGS, **kw)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CONFIGS])
+def test_convexify_matches_oracle(engines, name):
+    eng, st, params, x0 = engines[name]
+    f, J, b, obj = [t.cpu().numpy() for t in eng.convexify(params, x0)]
+    tol = 1e-7 if name == "arm" else 1e-9
+    for i in range(x0.shape[0]):
+        pp = sqp_port.PortProblem(st, params[i], x0[i])
+        pp.convexify()
+        Jd = helpers.split_J(st, J[i])
+        r0 = 0
+        for bi, blk in enumerate(st.blocks):
+            fo = pp.blocks[bi].f(pp.x)[:, 0]
+            np.testing.assert_allclose(f[i, r0:r0 + blk.m], fo, rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(Jd[bi], pp.J[bi], rtol=tol, atol=tol)
+            np.testing.assert_allclose(b[i, r0:r0 + blk.m], pp.b[bi][:, 0], rtol=tol, atol=tol * 10)
+            r0 += blk.m
+        assert abs(obj[i] - pp.objective(pp.x)) <= 1e-10 * max(1.0, abs(obj[i]))
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CONFIGS])
+@pytest.mark.parametrize("kdup,pi,delta", [(1, 1.0, 1.0), (3, 10.0, 0.1), (7, 1000.0, 2e-5)])
+def test_qp_stage_matches_oracle(engines, name, kdup, pi, delta):
+    eng, st, params, x0 = engines[name]
+    B = x0.shape[0]
+    f, J, b, _ = eng.convexify(params, x0)
+    Jn, bn = J.cpu().numpy(), b.cpu().numpy()
+    lbx, ubx = x0 - delta, x0 + delta
+    xq, status, iters = eng.qp_solve(params, _settings(), J=J, b=b, lbx=lbx, ubx=ubx,
+                                     pi=np.full(B, pi), kdup=np.full(B, kdup, np.int32))
+    xq, status, iters = xq.cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy()
+    for i in range(B):
+        Jd = helpers.split_J(st, Jn[i])
+        bl, r0 = [], 0
+        for blk in st.blocks:
+            bl.append(bn[i, r0:r0 + blk.m])
+            r0 += blk.m
+        masks = [np.ones_like(Jb, dtype=bool) for Jb in Jd]
+        P, q, A, l, u = helpers.expand_qp(st, params[i], Jd, bl, masks, lbx[i], ubx[i], pi, kdup)
+        res = helpers.oracle_qp(P, q, A, l, u)
+        assert status[i] == res.info.status_val, (i, status[i], res.info.status_val, iters[i], res.info.iter)
+        assert iters[i] == res.info.iter, (i, iters[i], res.info.iter)
+        if res.info.status_val in (1, 2, -2):
+            err = np.abs(xq[i] - res.x).max()
+            assert err <= 1e-7 * max(1.0, np.abs(res.x).max()), (i, err)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CONFIGS])
+def test_closest_point_qp_matches_oracle(engines, name):
+    eng, st, params, x0 = engines[name]
+    B = x0.shape[0]
+    xq, status, iters = eng.qp_solve(params, _settings(), xref=x0, use_penalty=False, closest_point=True)
+    xq, status, iters = xq.cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy()
+    inf = np.full(st.n, np.inf)
+    for i in range(B):
+        P, q, A, l, u = helpers.expand_qp(st, params[i], [], [], [], -inf, inf, 0.0, 0,
+                                          closest_xref=x0[i], use_penalty=False)
+        res = helpers.oracle_qp(P, q, A, l, u)
+        assert status[i] == res.info.status_val
+        assert iters[i] == res.info.iter
+        assert np.abs(xq[i] - res.x).max() <= 1e-7 * max(1.0, np.abs(res.x).max())
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CONFIGS])
+def test_full_solve_matches_port(engines, name):
+    eng, st, params, x0 = engines[name]
+    out = eng.solve_batch(params, x0, _settings())
+    x = out["x"].cpu().numpy()
+    verdict = out["verdict"].cpu().numpy()
+    vio = out["max_vio"].cpu().numpy()
+    obj = out["objective"].cpu().numpy()
+    stats = out["stats"].cpu().numpy()
+    for i in range(x0.shape[0]):
+        ref = sqp_port.solve(st, params[i], x0[i], solver=W.SOLVER_SETTINGS)
+        info = (name, i, stats[i].tolist(), ref["stats"])
+        assert (verdict[i] == 1) == ref["success"], info
+        err = np.abs(x[i] - ref["x"]).max()
+        assert err <= 1e-4 * max(1.0, np.abs(ref["x"]).max()), info + (err,)
+        assert abs(vio[i] - ref["max_vio"]) <= 1e-5, info
+        assert abs(obj[i] - ref["objective"]) <= 1e-5 * max(1.0, abs(ref["objective"])), info
