@@ -186,6 +186,11 @@ int sco_merit(sco_handle *h, int64_t B, const double *d_params, const double *d_
               const double *d_b, const double *d_mu, double *d_merit, double *d_model,
               double *d_max_vio, double *d_gv, double *d_gm, void *stream);
 
+/* ---- measurement helper (bench.py): sustained FP64 FMA rate of the device in TFLOP/s, the
+ * compute roofline of the shared-memory-resident ADMM kernel.  Not on the solve path; the
+ * reference has no counterpart. */
+int sco_probe_fp64(int device, double *tflops_out);
+
 #ifdef __cplusplus
 }
 #endif

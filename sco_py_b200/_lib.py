@@ -49,7 +49,8 @@ class CSettings(ctypes.Structure):
 
 
 EXPORTS = ["sco_last_error", "sco_default_settings", "sco_create", "sco_destroy", "sco_query",
-           "sco_solve_batch", "sco_solve_batch_host", "sco_convexify", "sco_qp_solve", "sco_merit"]
+           "sco_solve_batch", "sco_solve_batch_host", "sco_convexify", "sco_qp_solve", "sco_merit",
+           "sco_probe_fp64"]
 
 _lib = None
 
@@ -81,6 +82,7 @@ def load():
                                  c_vp, c_vp]
     lib.sco_merit.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                               c_vp]
+    lib.sco_probe_fp64.argtypes = [ctypes.c_int, ctypes.POINTER(c_dbl)]
     _lib = lib
     return lib
 

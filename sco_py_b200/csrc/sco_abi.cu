@@ -1,7 +1,7 @@
-// sco_abi.cu -- kernels + the C ABI declared in include/sco_b200.h.
-//
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
-//        -Iinclude sco_py_b200/csrc/sco_abi.cu -o sco_py_b200/libsco_b200.so
+// sco_abi.cu -- host side of the C ABI declared in include/sco_b200.h: the structure compiler
+// (index arrays, shared-memory layout, team size) and the launch wrappers.  The kernels live in
+// sco_kernels.cuh and are instantiated per team size by sco_team.cu.
+// Build: python -m sco_py_b200.build  (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3).
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -10,9 +10,7 @@
 
 #include "sco_b200.h"
 #include "sco_device.cuh"
-#include "sco_families.cuh"
-#include "sco_qp.cuh"
-#include "sco_sqp.cuh"
+#include "sco_launch.h"
 
 // ------------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -33,176 +31,11 @@ static int fail(int code, const char *fmt, ...) {
 
 extern "C" const char *sco_last_error(void) { return g_err; }
 
-// ------------------------------------------------------------------------------------ kernels
-template <int TEAM>
-__global__ void __launch_bounds__(TEAM)
-k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st, long long B,
-        const double *__restrict__ params, const double *__restrict__ x0, double *__restrict__ x_out,
-        int *__restrict__ verdict, double *__restrict__ merit, double *__restrict__ objective,
-        double *__restrict__ max_vio, int *__restrict__ stats, double *__restrict__ Jscr,
-        unsigned long long *counter) {
-  extern __shared__ double sm[];
-  __shared__ long long next;
-  QPW w;
-  w.bind(sm, S.L);
-  double *xc = sm + S.L.total;  // n doubles appended after the layout
-  double *Jg = Jscr + (size_t)blockIdx.x * S.jnnz;
-  const int tid = threadIdx.x;
-  while (true) {
-    if (tid == 0) next = (long long)atomicAdd(counter, 1ull);
-    Team<TEAM>::sync();
-    const long long b = next;
-    Team<TEAM>::sync();
-    if (b >= B) break;
-    const double *prm = params + b * S.stride;
-    SqpSolver<TEAM> sq(S, st, w, prm, xc, Jg);
-    SqpOut o = sq.run(x0 + b * S.n);
-    for (int j = tid; j < S.n; j += TEAM) x_out[b * S.n + j] = xc[j];
-    if (tid == 0) {
-      verdict[b] = o.verdict;
-      if (merit) merit[b] = o.merit;
-      if (objective) objective[b] = o.objective;
-      if (max_vio) max_vio[b] = o.max_vio;
-      if (stats) {
-        stats[4 * b] = o.sqp_iters; stats[4 * b + 1] = o.qp_solves;
-        stats[4 * b + 2] = o.admm_iters; stats[4 * b + 3] = o.last_status;
-      }
-    }
-    Team<TEAM>::sync();
-  }
-}
-
-template <int TEAM>
-__global__ void __launch_bounds__(TEAM)
-k_convexify(const __grid_constant__ DevStruct S, long long B, const double *__restrict__ params,
-            const double *__restrict__ x, double *__restrict__ f, double *__restrict__ J,
-            double *__restrict__ bvec, double *__restrict__ obj, double *__restrict__ Jscr) {
-  extern __shared__ double sm[];
-  QPW w;
-  w.bind(sm, S.L);
-  double *xc = sm + S.L.total;
-  const int tid = threadIdx.x;
-  DevSettings st;
-  memset(&st, 0, sizeof(st));
-  st.freeze_sparsity = 1;
-  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
-    const double *prm = params + b * S.stride;
-    double *Jg = J ? J + b * S.jnnz : Jscr + (size_t)blockIdx.x * S.jnnz;
-    SqpSolver<TEAM> sq(S, st, w, prm, xc, Jg);
-    for (int j = tid; j < S.n; j += TEAM) xc[j] = x[b * S.n + j];
-    Team<TEAM>::sync();
-    bool mask_set = false;
-    sq.convexify(mask_set);
-    for (int i = tid; i < S.m_nl; i += TEAM) {
-      if (f) f[b * S.m_nl + i] = w.fv[i];
-      if (bvec) bvec[b * S.m_nl + i] = w.bb[i];
-    }
-    if (obj) {
-      const double ov = sq.objective();
-      if (tid == 0) obj[b] = ov;
-    }
-    Team<TEAM>::sync();
-  }
-}
-
-template <int TEAM>
-__global__ void __launch_bounds__(TEAM)
-k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st, long long B,
-     const double *__restrict__ params, const double *__restrict__ J, const double *__restrict__ bvec,
-     const uint32_t *__restrict__ mask, const double *__restrict__ lbx, const double *__restrict__ ubx,
-     const double *__restrict__ pi, const int *__restrict__ kdup, const double *__restrict__ xref,
-     int use_pen, int closest, double *__restrict__ xq, int *__restrict__ status,
-     int *__restrict__ iters) {
-  extern __shared__ double sm[];
-  QPW w;
-  w.bind(sm, S.L);
-  const int tid = threadIdx.x;
-  const int n = S.n, ms = S.m_nl;
-  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
-    for (int j = tid; j < n; j += TEAM) {
-      w.lb[j] = lbx ? lbx[b * n + j] : -INFINITY;
-      w.ub[j] = ubx ? ubx[b * n + j] : INFINITY;
-      w.xs[j] = xref ? xref[b * n + j] : 0.0;
-    }
-    if (use_pen)
-      for (int i = tid; i < ms; i += TEAM) {
-        w.bb[i] = bvec[b * ms + i];
-        w.msk[i] = mask ? mask[b * ms + i] : 0xffffffffu;
-      }
-    Team<TEAM>::sync();
-    QPArgs a;
-    a.prm = params + b * S.stride;
-    a.Jg = use_pen ? J + b * S.jnnz : nullptr;
-    a.pi = pi ? pi[b] : 0.0;
-    a.kd = kdup ? (double)kdup[b] : 1.0;
-    a.use_pen = use_pen;
-    a.closest = closest;
-    QPSolver<TEAM> qp(S, st, w, a);
-    QPResult r = qp.solve();
-    const int nq = use_pen ? S.n_q : n;
-    for (int j = tid; j < n; j += TEAM) xq[b * nq + j] = w.x[j];
-    if (use_pen) {
-      int so = n;
-      for (int bi = 0; bi < S.n_blocks; bi++) {
-        const DevBlock &Bk = S.blocks[bi];
-        for (int r2 = tid; r2 < Bk.m; r2 += TEAM) {
-          xq[b * nq + so + r2] = w.s[Bk.row0 + r2];
-          if (Bk.cnt_type) xq[b * nq + so + Bk.m + r2] = w.s[ms + Bk.row0 + r2];
-        }
-        so += Bk.m * (Bk.cnt_type ? 2 : 1);
-      }
-    }
-    if (tid == 0) {
-      status[b] = r.status;
-      iters[b] = r.iters;
-    }
-    Team<TEAM>::sync();
-  }
-}
-
-template <int TEAM>
-__global__ void __launch_bounds__(TEAM)
-k_merit(const __grid_constant__ DevStruct S, long long B, const double *__restrict__ params,
-        const double *__restrict__ x, const double *__restrict__ J, const double *__restrict__ bvec,
-        const double *__restrict__ mu, double *__restrict__ merit, double *__restrict__ model,
-        double *__restrict__ max_vio, double *__restrict__ gv, double *__restrict__ gm) {
-  extern __shared__ double sm[];
-  QPW w;
-  w.bind(sm, S.L);
-  double *xc = sm + S.L.total;
-  const int tid = threadIdx.x;
-  DevSettings st;
-  memset(&st, 0, sizeof(st));
-  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
-    const double *prm = params + b * S.stride;
-    SqpSolver<TEAM> sq(S, st, w, prm, xc, const_cast<double *>(J ? J + b * S.jnnz : nullptr));
-    for (int j = tid; j < S.n; j += TEAM) xc[j] = x[b * S.n + j];
-    if (bvec)
-      for (int i = tid; i < S.m_nl; i += TEAM) w.bb[i] = bvec[b * S.m_nl + i];
-    Team<TEAM>::sync();
-    eval_blocks<TEAM>(S, prm, xc, w.fv, nullptr, w.stage);
-    double vs[2 + SCO_DEV_MAX_GROUPS], msum[2 + SCO_DEV_MAX_GROUPS];
-    sq.violation_sums(vs);
-    const double ov = sq.objective();
-    const double m = mu ? mu[b] : 1.0;
-    if (J && bvec) sq.model_sums(msum);
-    if (tid == 0) {
-      if (merit) merit[b] = ov + m * vs[0];
-      if (max_vio) max_vio[b] = vs[1];
-      if (model && J && bvec) model[b] = ov + m * msum[0];
-      for (int g = 0; g < S.n_groups; g++) {
-        if (gv) gv[b * S.n_groups + g] = vs[2 + g];
-        if (gm && J && bvec) gm[b * S.n_groups + g] = msum[2 + g];
-      }
-    }
-    Team<TEAM>::sync();
-  }
-}
-
 // ------------------------------------------------------------------------------------ handle
 struct sco_handle {
   int device = 0;
   int team = 32;
+  const TeamOps *ops = nullptr;
   int sm_count = 0;
   int occupancy = 1;
   size_t smem_bytes = 0;
@@ -261,19 +94,6 @@ static void build_layout(DevStruct &S, int team) {
   L.msk = take((mp + 1) / 2);
   L.stage = take(std::max((team / 32) * S.stage_per_warp, 100));
   L.total = off;
-}
-
-template <int TEAM>
-static int configure(sco_handle *h) {
-  const size_t bytes = h->smem_bytes;
-  CUDA_TRY(cudaFuncSetAttribute(k_solve<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_convexify<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_qp<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  CUDA_TRY(cudaFuncSetAttribute(k_merit<TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve<TEAM>, TEAM, bytes));
-  h->occupancy = std::max(occ, 1);
-  return 0;
 }
 
 extern "C" void sco_default_settings(sco_settings *s) {
@@ -472,8 +292,16 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
                 h->smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
   }
   h->team = team;
-  int crc = team == 32 ? configure<32>(h) : team == 64 ? configure<64>(h) : team == 128 ? configure<128>(h) : configure<256>(h);
-  if (crc) { sco_destroy(h); return crc; }
+  h->ops = team == 32 ? sco_team_ops_32() : team == 64 ? sco_team_ops_64() : team == 128 ? sco_team_ops_128() : sco_team_ops_256();
+  {
+    int occ = 0;
+    cudaError_t ce = h->ops->configure(h->smem_bytes, &occ);
+    if (ce != cudaSuccess) {
+      sco_destroy(h);
+      return fail(SCO_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(ce));
+    }
+    h->occupancy = std::max(occ, 1);
+  }
   h->Jscr_ctas = (size_t)h->sm_count * h->occupancy;
   if (cudaMalloc(&h->Jscr, std::max<size_t>(h->Jscr_ctas * std::max(jnnz, 1), 1) * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->counter, sizeof(unsigned long long)) != cudaSuccess) {
@@ -502,16 +330,6 @@ extern "C" int sco_query(sco_handle *h, int64_t *out8) {
   return SCO_OK;
 }
 
-#define DISPATCH(KERNEL, GRID, STREAM, ...)                                                        \
-  do {                                                                                             \
-    switch (h->team) {                                                                             \
-      case 32: KERNEL<32><<<GRID, 32, h->smem_bytes, STREAM>>>(__VA_ARGS__); break;                \
-      case 64: KERNEL<64><<<GRID, 64, h->smem_bytes, STREAM>>>(__VA_ARGS__); break;                \
-      case 128: KERNEL<128><<<GRID, 128, h->smem_bytes, STREAM>>>(__VA_ARGS__); break;             \
-      default: KERNEL<256><<<GRID, 256, h->smem_bytes, STREAM>>>(__VA_ARGS__); break;              \
-    }                                                                                              \
-  } while (0)
-
 extern "C" int sco_solve_batch(sco_handle *h, int64_t B, const double *d_params, const double *d_x0,
                                const sco_settings *s, double *d_x_out, int32_t *d_verdict,
                                double *d_merit, double *d_objective, double *d_max_vio,
@@ -523,8 +341,9 @@ extern "C" int sco_solve_batch(sco_handle *h, int64_t B, const double *d_params,
   DevSettings d = to_dev(s);
   CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
   const long long grid = std::min<long long>(B, (long long)h->Jscr_ctas);
-  DISPATCH(k_solve, (unsigned)grid, st, h->S, d, (long long)B, d_params, d_x0, d_x_out, d_verdict, d_merit,
-           d_objective, d_max_vio, d_stats, h->Jscr, h->counter);
+  SolveArgs a = {(long long)B, d_params, d_x0, d_x_out, d_verdict, d_merit, d_objective, d_max_vio, d_stats,
+                 h->Jscr, h->counter};
+  h->ops->solve((unsigned)grid, h->smem_bytes, st, h->S, d, a);
   CUDA_TRY(cudaGetLastError());
   return SCO_OK;
 }
@@ -579,7 +398,8 @@ extern "C" int sco_convexify(sco_handle *h, int64_t B, const double *d_params, c
   if (B <= 0) return SCO_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH(k_convexify, stage_grid(h, B), st, h->S, (long long)B, d_params, d_x, d_f, d_J, d_b, d_obj, h->Jscr);
+  ConvexifyArgs a = {(long long)B, d_params, d_x, d_f, d_J, d_b, d_obj, h->Jscr};
+  h->ops->convexify(stage_grid(h, B), h->smem_bytes, st, h->S, a);
   CUDA_TRY(cudaGetLastError());
   return SCO_OK;
 }
@@ -597,8 +417,9 @@ extern "C" int sco_qp_solve(sco_handle *h, int64_t B, const double *d_params, co
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   DevSettings d = to_dev(s);
-  DISPATCH(k_qp, stage_grid(h, B), st, h->S, d, (long long)B, d_params, d_J, d_b, d_mask, d_lbx, d_ubx, d_pi,
-           d_kdup, d_xref, use_penalty, closest_point, d_xq, d_status, d_iters);
+  QpStageArgs a = {(long long)B, d_params, d_J, d_b, d_mask, d_lbx, d_ubx, d_pi, d_kdup, d_xref,
+                   use_penalty, closest_point, d_xq, d_status, d_iters};
+  h->ops->qp(stage_grid(h, B), h->smem_bytes, st, h->S, d, a);
   CUDA_TRY(cudaGetLastError());
   return SCO_OK;
 }
@@ -610,8 +431,8 @@ extern "C" int sco_merit(sco_handle *h, int64_t B, const double *d_params, const
   if (B <= 0) return SCO_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH(k_merit, stage_grid(h, B), st, h->S, (long long)B, d_params, d_x, d_J, d_b, d_mu, d_merit, d_model,
-           d_max_vio, d_gv, d_gm);
+  MeritArgs a = {(long long)B, d_params, d_x, d_J, d_b, d_mu, d_merit, d_model, d_max_vio, d_gv, d_gm};
+  h->ops->merit(stage_grid(h, B), h->smem_bytes, st, h->S, a);
   CUDA_TRY(cudaGetLastError());
   return SCO_OK;
 }

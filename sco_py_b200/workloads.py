@@ -174,3 +174,35 @@ def gen_arm(B, T=20, seed_base=3000, first=0, fk=None):
 
 
 GENERATORS = {"qcqp": gen_qcqp, "point_robot": gen_point_robot, "arm": gen_arm}
+
+
+def _gen_chunk(args):
+    name, first, count, kw = args
+    _, params, x0 = GENERATORS[name](count, first=first, **kw)
+    return first, params, x0
+
+
+def gen_batch(name, B, first=0, workers=None, out_params=None, out_x0=None, **kw):
+    """Problems [first, first+B) of a config, generated by a process pool (per-problem seeds make
+    chunks independent).  `out_params` / `out_x0` may be preallocated (e.g. pinned) arrays."""
+    import multiprocessing as mp
+    import os
+    st = GENERATORS[name](1, first=first, **kw)[0]
+    params = out_params if out_params is not None else np.empty((B, st.stride))
+    x0 = out_x0 if out_x0 is not None else np.empty((B, st.n))
+    workers = workers or min(os.cpu_count() or 1, 32)
+    chunk = max(64, (B + 4 * workers - 1) // (4 * workers))
+    jobs = [(name, first + s, min(chunk, B - s), kw) for s in range(0, B, chunk)]
+    if workers <= 1 or len(jobs) == 1:
+        results = map(_gen_chunk, jobs)
+        pool = None
+    else:
+        pool = mp.get_context("fork").Pool(workers)
+        results = pool.imap_unordered(_gen_chunk, jobs)
+    for f, p, x in results:
+        params[f - first:f - first + p.shape[0]] = p
+        x0[f - first:f - first + p.shape[0]] = x
+    if pool is not None:
+        pool.close()
+        pool.join()
+    return st, params, x0
