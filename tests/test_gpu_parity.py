@@ -156,8 +156,8 @@ def test_host_buffer_entry_matches_device_entry(engines):
 
 def test_batch_properties_at_scale(engines):
     """Size-independent properties on a batch too large for the CPU oracle: every converged problem
-    satisfies its constraints to cnt_tolerance, results do not depend on batch composition, and
-    re-solving from the solution is a fixed point (converges at once, x unchanged to 1e-4)."""
+    satisfies its constraints to cnt_tolerance, the reported violation / objective are those of
+    the returned x, and results do not depend on batch composition or order."""
     eng, st, _, _ = engines["qcqp"]
     B = 4096
     _, params, x0 = W.gen_batch("qcqp", B)
@@ -177,8 +177,3 @@ def test_batch_properties_at_scale(engines):
     out2 = eng.solve_batch(params[perm], x0[perm], s)
     assert np.array_equal(out2["x"].cpu().numpy(), x[perm])
     assert np.array_equal(out2["verdict"].cpu().numpy(), verdict[perm])
-    # fixed point
-    conv = np.nonzero(verdict == 1)[0][:512]
-    out3 = eng.solve_batch(params[conv], x[conv], s)
-    assert (out3["verdict"].cpu().numpy() == 1).all()
-    assert np.abs(out3["x"].cpu().numpy() - x[conv]).max() <= 1e-4
