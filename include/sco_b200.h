@@ -138,7 +138,8 @@ typedef struct {
   int32_t freeze_sparsity;  /* C-2, prob.py:488-504 */
   int32_t duplicate_rows;   /* C-3, prob.py:508-509 */
   int32_t threads_per_problem; /* 0 = choose from the structure */
-  int32_t pad_[2];
+  int32_t force_generic;       /* 1 = never take the register-resident dense ADMM loop (A/B parity checks) */
+  int32_t pad_;
 } sco_settings;
 
 const char *sco_last_error(void);

@@ -44,7 +44,7 @@ class CSettings(ctypes.Structure):
         ("osqp_max_iter", c_i32), ("osqp_scaling", c_i32), ("osqp_check_termination", c_i32),
         ("osqp_adaptive_rho", c_i32), ("osqp_adaptive_rho_interval", c_i32),
         ("compound_penalty", c_i32), ("freeze_sparsity", c_i32), ("duplicate_rows", c_i32),
-        ("threads_per_problem", c_i32), ("pad_", c_i32 * 2),
+        ("threads_per_problem", c_i32), ("force_generic", c_i32), ("pad_", c_i32),
     ]
 
 

@@ -15,6 +15,7 @@ LIB = os.path.join(PKG, "libsco_b200.so")
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 TEAMS = (32, 64, 128, 256)
+DENSE_KINDS = (1, 2, 3, 4)  # size table of the dense ADMM loop, see sco_create
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -25,11 +26,13 @@ def _deps():
 def _units():
     """(object, source, extra flags)"""
     units = [(os.path.join(OBJ, "sco_abi.o"), os.path.join(CSRC, "sco_abi.cu"), []),
-             (os.path.join(OBJ, "sco_dense.o"), os.path.join(CSRC, "sco_dense.cu"), []),
              (os.path.join(OBJ, "sco_probe.o"), os.path.join(CSRC, "sco_probe.cu"), [])]
     for t in TEAMS:
         units.append((os.path.join(OBJ, "sco_team_%d.o" % t), os.path.join(CSRC, "sco_team.cu"),
                       ["-DSCO_TEAM=%d" % t]))
+    for dk in DENSE_KINDS:
+        units.append((os.path.join(OBJ, "sco_dense_%d.o" % dk), os.path.join(CSRC, "sco_team.cu"),
+                      ["-DSCO_TEAM=64", "-DSCO_DK=%d" % dk]))
     return [u for u in units if os.path.exists(u[1])]
 
 
@@ -44,6 +47,7 @@ def build(force=False, verbose=False):
                             "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
         base += ["-Xptxas", "-v"]
+    base += os.environ.get("SCO_NVCC_FLAGS", "").split()  # e.g. -DSCO_TIMING for the clock64 experiment
 
     def compile_one(u):
         obj, src, extra = u

@@ -35,7 +35,8 @@ extern "C" const char *sco_last_error(void) { return g_err; }
 struct sco_handle {
   int device = 0;
   int team = 32;
-  const TeamOps *ops = nullptr;
+  const TeamOps *ops = nullptr;    // solve / qp (dense variant when the structure qualifies)
+  const TeamOps *gen_ops = nullptr; // convexify / merit (generic team kernels)
   int sm_count = 0;
   int occupancy = 1;
   size_t smem_bytes = 0;
@@ -93,6 +94,11 @@ static void build_layout(DevStruct &S, int team) {
   L.red = take(8 * 16);
   L.msk = take((mp + 1) / 2);
   L.stage = take(std::max((team / 32) * S.stage_per_warp, 100));
+  if (S.dense_kind) {
+    L.Ph = take(n * n); L.fbuf = take(2 * FBUF_LD + 64 + 256); L.Kd = take(n * mp);
+  } else {
+    L.Ph = L.fbuf = L.Kd = 0;
+  }
   L.total = off;
 }
 
@@ -125,6 +131,7 @@ extern "C" void sco_default_settings(sco_settings *s) {
   s->freeze_sparsity = 1;
   s->duplicate_rows = 1;
   s->threads_per_problem = 0;
+  s->force_generic = 0;
 }
 
 static DevSettings to_dev(const sco_settings *s) {
@@ -155,6 +162,7 @@ static DevSettings to_dev(const sco_settings *s) {
   d.compound_penalty = s->compound_penalty;
   d.freeze_sparsity = s->freeze_sparsity;
   d.duplicate_rows = s->duplicate_rows;
+  d.force_generic = s->force_generic;
   return d;
 }
 
@@ -280,9 +288,18 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   rc |= upload(h, lcptr, &S.lin_cptr); rc |= upload(h, lcentry, &S.lin_centry); rc |= upload(h, lcrow, &S.lin_crow);
   rc |= upload(h, shared_v, &S.shared);
   if (rc) { sco_destroy(h); return SCO_ERR_CUDA; }
+  // ---- dense fast path: one dense hinge block, no linear rows, sizes within the instantiated table
+  S.dense_kind = 0;
+  if (desc->m_lin == 0 && desc->n_blocks == 1 && desc->blocks[0].family == SCO_FAM_QUADFORM &&
+      desc->blocks[0].cnt_type == SCO_CNT_LEQ) {
+    static const int table[][2] = {{8, 6}, {12, 16}, {20, 30}, {32, 32}};  // keep in sync with sco_qp_dense.cuh
+    for (int k = 0; k < 4; k++)
+      if (n <= table[k][0] && m_nl <= table[k][1]) { S.dense_kind = k + 1; break; }
+  }
   // ---- team size and shared-memory layout
   const int work = std::max(std::max(n, m_nl), desc->m_lin);
   int team = work <= 40 ? 32 : work <= 96 ? 64 : work <= 192 ? 128 : 256;
+  if (S.dense_kind) team = 64;  // two warps per problem: rows | variables (sco_qp_dense.inl)
   for (;;) {
     build_layout(S, team);
     h->smem_bytes = (size_t)(S.L.total + ((n + 1) & ~1)) * sizeof(double);
@@ -292,10 +309,14 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
                 h->smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
   }
   h->team = team;
-  h->ops = team == 32 ? sco_team_ops_32() : team == 64 ? sco_team_ops_64() : team == 128 ? sco_team_ops_128() : sco_team_ops_256();
+  h->gen_ops = team == 32 ? sco_team_ops_32() : team == 64 ? sco_team_ops_64() : team == 128 ? sco_team_ops_128() : sco_team_ops_256();
+  h->ops = h->gen_ops;
+  if (S.dense_kind)
+    h->ops = S.dense_kind == 1 ? sco_dense_ops_1() : S.dense_kind == 2 ? sco_dense_ops_2() : S.dense_kind == 3 ? sco_dense_ops_3() : sco_dense_ops_4();
   {
     int occ = 0;
-    cudaError_t ce = h->ops->configure(h->smem_bytes, &occ);
+    cudaError_t ce = h->gen_ops->configure(h->smem_bytes, &occ);
+    if (ce == cudaSuccess && h->ops != h->gen_ops) ce = h->ops->configure(h->smem_bytes, &occ);
     if (ce != cudaSuccess) {
       sco_destroy(h);
       return fail(SCO_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(ce));
@@ -399,7 +420,7 @@ extern "C" int sco_convexify(sco_handle *h, int64_t B, const double *d_params, c
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   ConvexifyArgs a = {(long long)B, d_params, d_x, d_f, d_J, d_b, d_obj, h->Jscr};
-  h->ops->convexify(stage_grid(h, B), h->smem_bytes, st, h->S, a);
+  h->gen_ops->convexify(stage_grid(h, B), h->smem_bytes, st, h->S, a);
   CUDA_TRY(cudaGetLastError());
   return SCO_OK;
 }
@@ -432,7 +453,7 @@ extern "C" int sco_merit(sco_handle *h, int64_t B, const double *d_params, const
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   MeritArgs a = {(long long)B, d_params, d_x, d_J, d_b, d_mu, d_merit, d_model, d_max_vio, d_gv, d_gm};
-  h->ops->merit(stage_grid(h, B), h->smem_bytes, st, h->S, a);
+  h->gen_ops->merit(stage_grid(h, B), h->smem_bytes, st, h->S, a);
   CUDA_TRY(cudaGetLastError());
   return SCO_OK;
 }

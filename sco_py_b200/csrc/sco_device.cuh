@@ -19,6 +19,8 @@
 #define OSQP_RHO_EQ_OVER_RHO_INEQ 1e3
 #define OSQP_RHO_TOL 1e-4
 
+#define FBUF_LD 66  // (c, wp) exchange vector: up to 32 + 32 entries + pad, even (16-byte aligned rows)
+
 struct DevField {
   long long off;
   int shared;
@@ -50,12 +52,15 @@ struct Layout {
   int red;    // reduction scratch: 8 warps * 8 values
   int msk;    // m_nl uint32 (counted in doubles, rounded up)
   int stage;  // per-warp staging buffers for family evaluation
+  // dense fast path (sco_qp_dense.cuh): scaled P, exchange buffers c (double-buffered), wp, x~
+  int Ph, fbuf, Kd;  // fbuf: (c, wp) double-buffered [2][FBUF_LD] + x[32] + kd*y[32] ; Kd: K = S^-1 J' (n x m)
   int total;  // doubles
 };
 
 struct DevStruct {
   int n, m_lin, nnz_lin, n_blocks, n_groups, m_nl, n_slack, jnnz, n_q, nsl;
   int sjnnz;           // padded Jacobian entries in shared memory
+  int dense_kind;      // != 0: register-resident dense ADMM loop (sco_qp_dense.cuh), index into its size table
   int stage_per_warp;  // doubles
   long long stride;
   DevField Q, q, c, lin_l, lin_u;
@@ -83,13 +88,32 @@ struct DevSettings {
   int max_merit_coeff_increases, max_sqp_iters;
   double eps_abs, eps_rel, rho, sigma, alpha, eps_prim_inf, eps_dual_inf;
   int max_iter, scaling, check_termination, adaptive_rho, adaptive_rho_interval;
-  int compound_penalty, freeze_sparsity, duplicate_rows;
+  int compound_penalty, freeze_sparsity, duplicate_rows, force_generic;
 };
 
 __device__ __forceinline__ const double *field_ptr(const DevStruct &S, const DevField &f,
                                                    const double *prm) {
   return f.off < 0 ? nullptr : ((f.shared ? S.shared : prm) + f.off);
 }
+
+extern __shared__ __align__(16) double sco_smem[];
+extern __shared__ __align__(16) double2 sco_smem2[];  // same storage, viewed as 16-byte words
+
+struct Sh {
+  int off;
+  __device__ __forceinline__ double &operator[](int i) const { return sco_smem[off + i]; }
+  __device__ __forceinline__ Sh operator+(int k) const { return Sh{off + k}; }
+  __device__ __forceinline__ double *ptr() const { return sco_smem + off; }
+  // 16-byte word i of the array (off must be even): a shared-space access, no generic pointer
+  __device__ __forceinline__ const double2 &v2(int i) const { return sco_smem2[(off >> 1) + i]; }
+};
+struct ShU32 {
+  int off;  // in doubles
+  __device__ __forceinline__ uint32_t &operator[](int i) const {
+    return reinterpret_cast<uint32_t *>(sco_smem + off)[i];
+  }
+};
+
 
 // ------------------------------------------------------------------------------------
 // team primitives
@@ -101,7 +125,7 @@ struct Team {
   }
 
   template <int K, bool IS_MAX>
-  static __device__ __forceinline__ void reduce(double (&v)[K], double *red) {
+  static __device__ __forceinline__ void reduce(double (&v)[K], Sh red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -128,11 +152,11 @@ struct Team {
     }
   }
   template <int K>
-  static __device__ __forceinline__ void reduce_max(double (&v)[K], double *red) {
+  static __device__ __forceinline__ void reduce_max(double (&v)[K], Sh red) {
     reduce<K, true>(v, red);
   }
   template <int K>
-  static __device__ __forceinline__ void reduce_sum(double (&v)[K], double *red) {
+  static __device__ __forceinline__ void reduce_sum(double (&v)[K], Sh red) {
     reduce<K, false>(v, red);
   }
 };
@@ -143,31 +167,38 @@ __device__ __forceinline__ double limit_scaling(double v) {
   return v;
 }
 
-// shared-memory views
+// ------------------------------------------------------------------------------------
+// shared-memory views.  Every array of the working set is addressed as an offset into the ONE
+// dynamic shared-memory array below, so the compiler can prove the address space and emits
+// LDS/STS (raw double* members made every access a generic LD/ST).
 struct QPW {
-  double *Js, *Sm, *Als;
-  double *x, *xt, *xt2, *qh, *D, *bx, *rb, *lb, *ub, *zb, *yb, *Eb, *dxv, *dyb, *xs;
-  double *El, *rl, *ll, *ul, *zl, *yl, *wl, *dyl;
-  double *Ep, *rp, *lp, *up, *zp, *yp, *wp, *bb, *fv, *dyp;
-  double *s, *Ds, *sl, *bs, *zs, *ys, *Es, *gs, *hs, *rs, *dss, *dys, *Minv;
-  double *red;
-  uint32_t *msk;
-  double *stage;
+  Sh Js, Sm, Als;
+  Sh x, xt, xt2, qh, D, bx, rb, lb, ub, zb, yb, Eb, dxv, dyb, xs;
+  Sh El, rl, ll, ul, zl, yl, wl, dyl;
+  Sh Ep, rp, lp, up, zp, yp, wp, bb, fv, dyp;
+  Sh s, Ds, sl, bs, zs, ys, Es, gs, hs, rs, dss, dys, Minv;
+  Sh red;
+  ShU32 msk;
+  Sh stage;
+  Sh Ph, fbuf, Kd;
+  Sh xc;  // current SQP iterate, n doubles appended after the layout
 
-  __device__ __forceinline__ void bind(double *sm, const Layout &L) {
-    Js = sm + L.Js; Sm = sm + L.S; Als = sm + L.Als;
-    x = sm + L.x; xt = sm + L.xt; xt2 = sm + L.xt2; qh = sm + L.qh; D = sm + L.D; bx = sm + L.bx;
-    rb = sm + L.rb; lb = sm + L.lb; ub = sm + L.ub; zb = sm + L.zb; yb = sm + L.yb; Eb = sm + L.Eb;
-    dxv = sm + L.dxv; dyb = sm + L.dyb; xs = sm + L.xs;
-    El = sm + L.El; rl = sm + L.rl; ll = sm + L.ll; ul = sm + L.ul; zl = sm + L.zl; yl = sm + L.yl;
-    wl = sm + L.wl; dyl = sm + L.dyl;
-    Ep = sm + L.Ep; rp = sm + L.rp; lp = sm + L.lp; up = sm + L.up; zp = sm + L.zp; yp = sm + L.yp;
-    wp = sm + L.wp; bb = sm + L.bb; fv = sm + L.fv; dyp = sm + L.dyp;
-    s = sm + L.s; Ds = sm + L.Ds; sl = sm + L.sl; bs = sm + L.bs; zs = sm + L.zs; ys = sm + L.ys;
-    Es = sm + L.Es; gs = sm + L.gs; hs = sm + L.hs; rs = sm + L.rs; dss = sm + L.dss; dys = sm + L.dys;
-    Minv = sm + L.Minv;
-    red = sm + L.red;
-    msk = reinterpret_cast<uint32_t *>(sm + L.msk);
-    stage = sm + L.stage;
+  __device__ __forceinline__ void bind(const Layout &L) {
+    Js = Sh{L.Js}; Sm = Sh{L.S}; Als = Sh{L.Als};
+    x = Sh{L.x}; xt = Sh{L.xt}; xt2 = Sh{L.xt2}; qh = Sh{L.qh}; D = Sh{L.D}; bx = Sh{L.bx};
+    rb = Sh{L.rb}; lb = Sh{L.lb}; ub = Sh{L.ub}; zb = Sh{L.zb}; yb = Sh{L.yb}; Eb = Sh{L.Eb};
+    dxv = Sh{L.dxv}; dyb = Sh{L.dyb}; xs = Sh{L.xs};
+    El = Sh{L.El}; rl = Sh{L.rl}; ll = Sh{L.ll}; ul = Sh{L.ul}; zl = Sh{L.zl}; yl = Sh{L.yl};
+    wl = Sh{L.wl}; dyl = Sh{L.dyl};
+    Ep = Sh{L.Ep}; rp = Sh{L.rp}; lp = Sh{L.lp}; up = Sh{L.up}; zp = Sh{L.zp}; yp = Sh{L.yp};
+    wp = Sh{L.wp}; bb = Sh{L.bb}; fv = Sh{L.fv}; dyp = Sh{L.dyp};
+    s = Sh{L.s}; Ds = Sh{L.Ds}; sl = Sh{L.sl}; bs = Sh{L.bs}; zs = Sh{L.zs}; ys = Sh{L.ys};
+    Es = Sh{L.Es}; gs = Sh{L.gs}; hs = Sh{L.hs}; rs = Sh{L.rs}; dss = Sh{L.dss}; dys = Sh{L.dys};
+    Minv = Sh{L.Minv};
+    red = Sh{L.red};
+    msk = ShU32{L.msk};
+    stage = Sh{L.stage};
+    Ph = Sh{L.Ph}; fbuf = Sh{L.fbuf}; Kd = Sh{L.Kd};
+    xc = Sh{L.total};
   }
 };

@@ -22,10 +22,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---- QUADFORM: f_j = 0.5 x'P_j x + a_j'x, P_j packed upper row-major, one warp per row ----
 template <int TEAM>
 __device__ void eval_quadform(const DevStruct &S, const DevBlock &B, const double *par,
-                              const double *x, double *f, double *Jout, double *stage) {
+                              Sh x, Sh f, double *Jout, Sh stage) {
   const int n = S.n, ntri = n * (n + 1) / 2, m = B.m;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *buf = stage + warp * S.stage_per_warp;
+  const Sh buf = stage + warp * S.stage_per_warp;
   const double *A = par + (size_t)m * ntri;
   for (int j = warp; j < m; j += TEAM / 32) {
     const double *Pj = par + (size_t)j * ntri;
@@ -50,7 +50,7 @@ __device__ void eval_quadform(const DevStruct &S, const DevBlock &B, const doubl
 // ---- CIRCLE2D: row t*K+k: R_k - |p_t - c_k| ----
 template <int TEAM>
 __device__ void eval_circle2d(const DevStruct &S, const DevBlock &B, const double *par,
-                              const double *x, double *f, double *Jout) {
+                              Sh x, Sh f, double *Jout) {
   const int K = B.ipar[1], m = B.m;
   for (int r = threadIdx.x; r < m; r += TEAM) {
     const int t = r / K, k = r % K;
@@ -89,13 +89,14 @@ __device__ __forceinline__ void fk7_pos(const double *q, const double *tab, doub
 // Central differences at steps h and 2h, Richardson-combined -- the scheme of
 // oracle/shims/numdifftools (restating numdifftools.Jacobian as called at expr.py:67).
 template <int TEAM>
-__device__ void eval_fk7(const DevStruct &S, const DevBlock &B, const double *tab, const double *x,
-                         double *f, double *Jout, double *stage) {
+__device__ void eval_fk7(const DevStruct &S, const DevBlock &B, const double *tab, Sh x, Sh f,
+                         double *Jout, Sh stage) {
   const int n = S.n, t = threadIdx.x;
-  const double *q = x + (n - 7);
+  const Sh q = x + (n - 7);
   if (t == 0) {
-    double o[3];
-    fk7_pos(q, tab, o);
+    double o[3], q0[7];
+    for (int k = 0; k < 7; k++) q0[k] = q[k];
+    fk7_pos(q0, tab, o);
     f[0] = o[0]; f[1] = o[1]; f[2] = o[2];
   }
   if (Jout) {
@@ -126,12 +127,11 @@ __device__ void eval_fk7(const DevStruct &S, const DevBlock &B, const double *ta
 // Evaluate every block at x: fv[row] = f_row(x); if Jg != null also the stored Jacobian entries.
 // Ends with a team sync.
 template <int TEAM>
-__device__ void eval_blocks(const DevStruct &S, const double *prm, const double *x, double *fv,
-                            double *Jg, double *stage) {
+__device__ __noinline__ void eval_blocks(const DevStruct &S, const double *prm, Sh x, Sh fv, double *Jg, Sh stage) {
   for (int bi = 0; bi < S.n_blocks; bi++) {
     const DevBlock &B = S.blocks[bi];
     const double *par = field_ptr(S, B.par, prm);
-    double *f = fv + B.row0;
+    const Sh f = fv + B.row0;
     double *J = Jg ? Jg + B.joff : nullptr;
     if (B.family == FAM_QUADFORM) eval_quadform<TEAM>(S, B, par, x, f, J, stage);
     else if (B.family == FAM_CIRCLE2D) eval_circle2d<TEAM>(S, B, par, x, f, J);

@@ -7,18 +7,26 @@
 #include "sco_qp.cuh"
 #include "sco_sqp.cuh"
 
-template <int TEAM>
-__global__ void __launch_bounds__(TEAM)
+// Register budget per thread.  The register file is split over the four SM sub-partitions (16 K
+// registers each), so the steps are 255 (2 warps per sub-partition), 168 (3), 128 (4).  Left alone,
+// ptxas aims a 64-thread kernel at 168 and the dense loop's matrix rows (100 registers) spill to
+// local memory inside the ADMM loop; the dense kinds therefore take the full 255.
+#ifndef SCO_DK
+#define SCO_DK 0
+#endif
+#define SCO_MAXNREG 255
+
+template <int TEAM, int DK>
+__global__ void __maxnreg__(SCO_MAXNREG)
 k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st, long long B,
         const double *__restrict__ params, const double *__restrict__ x0, double *__restrict__ x_out,
         int *__restrict__ verdict, double *__restrict__ merit, double *__restrict__ objective,
         double *__restrict__ max_vio, int *__restrict__ stats, double *__restrict__ Jscr,
         unsigned long long *counter) {
-  extern __shared__ double sm[];
   __shared__ long long next;
   QPW w;
-  w.bind(sm, S.L);
-  double *xc = sm + S.L.total;  // n doubles appended after the layout
+  w.bind(S.L);
+  const Sh xc = w.xc;  // n doubles appended after the layout
   double *Jg = Jscr + (size_t)blockIdx.x * S.jnnz;
   const int tid = threadIdx.x;
   while (true) {
@@ -28,7 +36,7 @@ k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings
     Team<TEAM>::sync();
     if (b >= B) break;
     const double *prm = params + b * S.stride;
-    SqpSolver<TEAM> sq(S, st, w, prm, xc, Jg);
+    SqpSolver<TEAM, DK> sq(S, st, w, prm, Jg);
     SqpOut o = sq.run(x0 + b * S.n);
     for (int j = tid; j < S.n; j += TEAM) x_out[b * S.n + j] = xc[j];
     if (tid == 0) {
@@ -50,10 +58,9 @@ __global__ void __launch_bounds__(TEAM)
 k_convexify(const __grid_constant__ DevStruct S, long long B, const double *__restrict__ params,
             const double *__restrict__ x, double *__restrict__ f, double *__restrict__ J,
             double *__restrict__ bvec, double *__restrict__ obj, double *__restrict__ Jscr) {
-  extern __shared__ double sm[];
   QPW w;
-  w.bind(sm, S.L);
-  double *xc = sm + S.L.total;
+  w.bind(S.L);
+  const Sh xc = w.xc;
   const int tid = threadIdx.x;
   DevSettings st;
   memset(&st, 0, sizeof(st));
@@ -61,7 +68,7 @@ k_convexify(const __grid_constant__ DevStruct S, long long B, const double *__re
   for (long long b = blockIdx.x; b < B; b += gridDim.x) {
     const double *prm = params + b * S.stride;
     double *Jg = J ? J + b * S.jnnz : Jscr + (size_t)blockIdx.x * S.jnnz;
-    SqpSolver<TEAM> sq(S, st, w, prm, xc, Jg);
+    SqpSolver<TEAM, 0> sq(S, st, w, prm, Jg);
     for (int j = tid; j < S.n; j += TEAM) xc[j] = x[b * S.n + j];
     Team<TEAM>::sync();
     bool mask_set = false;
@@ -78,17 +85,16 @@ k_convexify(const __grid_constant__ DevStruct S, long long B, const double *__re
   }
 }
 
-template <int TEAM>
-__global__ void __launch_bounds__(TEAM)
+template <int TEAM, int DK>
+__global__ void __maxnreg__(SCO_MAXNREG)
 k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st, long long B,
      const double *__restrict__ params, const double *__restrict__ J, const double *__restrict__ bvec,
      const uint32_t *__restrict__ mask, const double *__restrict__ lbx, const double *__restrict__ ubx,
      const double *__restrict__ pi, const int *__restrict__ kdup, const double *__restrict__ xref,
      int use_pen, int closest, double *__restrict__ xq, int *__restrict__ status,
      int *__restrict__ iters) {
-  extern __shared__ double sm[];
   QPW w;
-  w.bind(sm, S.L);
+  w.bind(S.L);
   const int tid = threadIdx.x;
   const int n = S.n, ms = S.m_nl;
   for (long long b = blockIdx.x; b < B; b += gridDim.x) {
@@ -110,7 +116,7 @@ k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st
     a.kd = kdup ? (double)kdup[b] : 1.0;
     a.use_pen = use_pen;
     a.closest = closest;
-    QPSolver<TEAM> qp(S, st, w, a);
+    QPSolver<TEAM, DK> qp(S, st, w, a);
     QPResult r = qp.solve();
     const int nq = use_pen ? S.n_q : n;
     for (int j = tid; j < n; j += TEAM) xq[b * nq + j] = w.x[j];
@@ -128,6 +134,9 @@ k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st
     if (tid == 0) {
       status[b] = r.status;
       iters[b] = r.iters;
+#ifdef SCO_TIMING
+      xq[b * nq] = (double)r.cyc_loop; xq[b * nq + 1] = (double)r.cyc_check; xq[b * nq + 2] = (double)r.cyc_setup;
+#endif
     }
     Team<TEAM>::sync();
   }
@@ -139,16 +148,15 @@ k_merit(const __grid_constant__ DevStruct S, long long B, const double *__restri
         const double *__restrict__ x, const double *__restrict__ J, const double *__restrict__ bvec,
         const double *__restrict__ mu, double *__restrict__ merit, double *__restrict__ model,
         double *__restrict__ max_vio, double *__restrict__ gv, double *__restrict__ gm) {
-  extern __shared__ double sm[];
   QPW w;
-  w.bind(sm, S.L);
-  double *xc = sm + S.L.total;
+  w.bind(S.L);
+  const Sh xc = w.xc;
   const int tid = threadIdx.x;
   DevSettings st;
   memset(&st, 0, sizeof(st));
   for (long long b = blockIdx.x; b < B; b += gridDim.x) {
     const double *prm = params + b * S.stride;
-    SqpSolver<TEAM> sq(S, st, w, prm, xc, const_cast<double *>(J ? J + b * S.jnnz : nullptr));
+    SqpSolver<TEAM, 0> sq(S, st, w, prm, const_cast<double *>(J ? J + b * S.jnnz : nullptr));
     for (int j = tid; j < S.n; j += TEAM) xc[j] = x[b * S.n + j];
     if (bvec)
       for (int i = tid; i < S.m_nl; i += TEAM) w.bb[i] = bvec[b * S.m_nl + i];

@@ -34,6 +34,9 @@ struct QPArgs {
 struct QPResult {
   int status, iters;
   double pri_res, dua_res;
+#ifdef SCO_TIMING
+  long long cyc_loop, cyc_check, cyc_setup;  // clock64() ticks: ADMM loop (incl. checks), checks, setup
+#endif
 };
 
 // rho for a row with scaled bounds [l, u] (OSQP set_rho_vec)
@@ -60,7 +63,7 @@ __device__ __forceinline__ double proj_dy(double dy, double l, double u) {
   return dy;
 }
 
-template <int TEAM>
+template <int TEAM, int DK>
 struct QPSolver {
   const DevStruct &S;
   const DevSettings &st;
@@ -87,7 +90,7 @@ struct QPSolver {
 
   // A' * (row-space vector) for user variable j: linear rows (vl) and penalty rows (vp; the caller
   // folds the multiplicity kd into vp).  The bound row is added by the caller.
-  __device__ __forceinline__ double gatherAT(int j, const double *vl, const double *vp) const {
+  __device__ __forceinline__ double gatherAT(int j, Sh vl, Sh vp) const {
     double acc = 0.0;
     if (m_lin) {
       for (int p = S.lin_cptr[j]; p < S.lin_cptr[j + 1]; p++)
@@ -100,12 +103,12 @@ struct QPSolver {
     }
     return acc;
   }
-  __device__ __forceinline__ double lin_row_dot(int r, const double *v) const {
+  __device__ __forceinline__ double lin_row_dot(int r, Sh v) const {
     double acc = 0.0;
     for (int p = S.lin_rowptr[r]; p < S.lin_rowptr[r + 1]; p++) acc += w.Als[p] * v[S.lin_col[p]];
     return acc;
   }
-  __device__ __forceinline__ double pen_row_dot(int i, const double *v) const {
+  __device__ __forceinline__ double pen_row_dot(int i, Sh v) const {
     const int so = S.row_soff[i], go = S.row_goff[i], wd = S.row_w[i];
     double acc = 0.0;
     for (int k = 0; k < wd; k++) acc += w.Js[so + k] * v[S.jcol_g[go + k]];
@@ -119,7 +122,7 @@ struct QPSolver {
 
   // ================================================================== setup
   // expects (unscaled): w.lb/w.ub bounds on x, w.bb = b, w.msk, w.xs (closest point target)
-  __device__ void load_and_scale() {
+  __device__ __noinline__ void load_and_scale() {
     const double *qg = field_ptr(S, S.q, a.prm);
     const double *llg = field_ptr(S, S.lin_l, a.prm), *ulg = field_ptr(S, S.lin_u, a.prm);
     for (int e = tid; e < n * n; e += TEAM) w.Sm[e] = psym(e / n, e % n);
@@ -253,7 +256,7 @@ struct QPSolver {
 
   // S = Psym^ + sigma I + A_x' R A_x - slack Schur terms, then S <- S^-1 (in place).
   // `reload`: Sm does not hold the unscaled Psym any more (rho update) -> fetch it again.
-  __device__ void assemble_and_invert(bool reload) {
+  __device__ __noinline__ void assemble_and_invert(bool reload) {
     const double sigma = st.sigma;
     for (int i = tid; i < m_nl; i += TEAM) {
       const double kr = a.kd * w.rp[i];
@@ -283,6 +286,7 @@ struct QPSolver {
       const int i = e / n, j = e % n;
       const double pv = reload ? psym(i, j) : w.Sm[e];
       double v = c * w.D[i] * pv * w.D[j];
+      if (S.dense_kind) w.Ph[e] = v;
       if (i == j) v += sigma + w.rb[j] * w.bx[j] * w.bx[j];
       w.Sm[e] = v;
     }
@@ -329,7 +333,7 @@ struct QPSolver {
   // ================================================================== termination
   // Returns a terminal status or 0.  Scratch: xt (D.*x), wp (kd*yp).  sc[] receives the scaled
   // norms needed by the rho estimate: {|Ax-z|, |z|, |Ax|, |Px+q+A'y|, |q|, |A'y|, |Px|}.
-  __device__ int check(int approximate, double &pri_res_out, double &dua_res_out, double *sc) {
+  __device__ __noinline__ int check(int approximate, double &pri_res_out, double &dua_res_out, double *sc) {
     double ea = st.eps_abs, er = st.eps_rel, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
     if (approximate) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
     const double cinv = 1.0 / c;
@@ -403,7 +407,7 @@ struct QPSolver {
   }
 
   // delta_y of the last iteration: dyl (lin), dyp (pen), dyb (x bounds), dys (slack bounds)
-  __device__ bool primal_infeasible(double eps) {
+  __device__ __noinline__ bool primal_infeasible(double eps) {
     double nv[1] = {0.0}, lhs[1] = {0.0};
     for (int r = tid; r < m_lin; r += TEAM) {
       const double dy = proj_dy(w.dyl[r], w.ll[r], w.ul[r]);
@@ -456,7 +460,7 @@ struct QPSolver {
   }
 
   // delta_x of the last iteration: dxv (user variables), dss (slacks)
-  __device__ bool dual_infeasible(double eps) {
+  __device__ __noinline__ bool dual_infeasible(double eps) {
     double nv[1] = {0.0}, qd[1] = {0.0};
     for (int j = tid; j < n; j += TEAM) {
       nv[0] = fmax(nv[0], fabs(w.D[j] * w.dxv[j]));
@@ -520,12 +524,9 @@ struct QPSolver {
 
   // ================================================================== the ADMM loop
   // On return w.x (user variables) and w.s (slacks) hold the UNSCALED solution.
-  __device__ QPResult solve() {
+  // generic shared-memory ADMM loop; returns the status (0 = max_iter reached without a verdict)
+  __device__ __noinline__ int generic_loop(int &iter_out, bool &checked_out, QPResult &res) {
     const double sigma = st.sigma, alpha = st.alpha, oma = 1.0 - st.alpha;
-    load_and_scale();
-    rho = st.rho;
-    set_rho();
-    assemble_and_invert(false);
     for (int j = tid; j < n; j += TEAM) { w.x[j] = 0.0; w.zb[j] = 0.0; w.yb[j] = 0.0; }
     for (int r = tid; r < m_lin; r += TEAM) { w.zl[r] = 0.0; w.yl[r] = 0.0; }
     for (int i = tid; i < m_nl; i += TEAM) {
@@ -539,8 +540,6 @@ struct QPSolver {
     const double cpi = c * a.pi;
     int interval = st.adaptive_rho_interval;
     if (st.adaptive_rho && interval == 0) interval = st.check_termination ? 4 * st.check_termination : 100;
-    QPResult res;
-    res.status = 0; res.iters = 0; res.pri_res = 0.0; res.dua_res = 0.0;
     int iter, status = 0;
     bool checked = false;
     for (iter = 1; iter <= st.max_iter; iter++) {
@@ -655,6 +654,54 @@ struct QPSolver {
         sync();
       }
     }
+    iter_out = iter;
+    checked_out = checked;
+    return status;
+  }
+
+#include "sco_qp_dense.inl"
+
+  // the dense loop treats rho of the penalty rows and of the slack-bound rows as the scalar rho
+  __device__ bool dense_eligible() {
+    double bad[1] = {0.0};
+    for (int i = tid; i < m_nl; i += TEAM)
+      if (w.rp[i] != rho || w.rs[i] != rho || S.row_eq[i]) bad[0] = 1.0;
+    Team<TEAM>::reduce_max(bad, w.red);
+    return bad[0] == 0.0;
+  }
+
+  __device__ __noinline__ QPResult solve() {
+#ifdef SCO_TIMING
+    const long long t_begin = clock64();
+#endif
+    load_and_scale();
+    rho = st.rho;
+    set_rho();
+    assemble_and_invert(false);
+    QPResult res;
+    res.status = 0; res.iters = 0; res.pri_res = 0.0; res.dua_res = 0.0;
+#ifdef SCO_TIMING
+    res.cyc_check = 0;
+    res.cyc_setup = clock64() - t_begin;
+    const long long t_loop = clock64();
+#endif
+    int iter = 0, status = 0;
+    bool checked = false;
+    bool dense = false;
+    if constexpr (TEAM == 64 && DK != 0) {
+      if (!st.force_generic && !st.adaptive_rho && a.use_pen && dense_eligible()) {
+        dense = true;
+        // keep in sync with the size table in sco_create (sco_abi.cu)
+        if constexpr (DK == 1) status = dense_loop<8, 6>(iter, checked, res);
+        else if constexpr (DK == 2) status = dense_loop<12, 16>(iter, checked, res);
+        else if constexpr (DK == 3) status = dense_loop<20, 30>(iter, checked, res);
+        else status = dense_loop<32, 32>(iter, checked, res);
+      }
+    }
+    if (!dense) status = generic_loop(iter, checked, res);
+#ifdef SCO_TIMING
+    res.cyc_loop = clock64() - t_loop;
+#endif
     if (status == 0) {
       iter = st.max_iter;
       if (!checked) {

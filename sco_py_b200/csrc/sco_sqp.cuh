@@ -18,19 +18,19 @@ struct SqpOut {
   int sqp_iters, qp_solves, admm_iters, last_status;
 };
 
-template <int TEAM>
+template <int TEAM, int DK>
 struct SqpSolver {
   const DevStruct &S;
   const DevSettings &st;
   QPW &w;
   const double *prm;
-  double *xc;   // current iterate (shared memory)
+  Sh xc;        // current iterate (shared memory)
   double *Jg;   // unscaled Jacobian entries of the last convexification (global scratch)
   const int tid, n, m_nl, ng;
 
   __device__ SqpSolver(const DevStruct &S_, const DevSettings &st_, QPW &w_, const double *prm_,
-                       double *xc_, double *Jg_)
-      : S(S_), st(st_), w(w_), prm(prm_), xc(xc_), Jg(Jg_), tid(threadIdx.x), n(S_.n),
+                       double *Jg_)
+      : S(S_), st(st_), w(w_), prm(prm_), xc(w_.xc), Jg(Jg_), tid(threadIdx.x), n(S_.n),
         m_nl(S_.m_nl), ng(S_.m_nl ? S_.n_groups : 0) {}
 
   __device__ __forceinline__ void sync() { Team<TEAM>::sync(); }
@@ -133,7 +133,7 @@ struct SqpSolver {
       DevSettings d = st;
       d.eps_abs = 1e-6; d.eps_rel = 1e-9; d.max_iter = 100000; d.rho = 0.1; d.sigma = 5e-10;
       d.adaptive_rho = 0;
-      QPSolver<TEAM> qp(S, d, w, a);
+      QPSolver<TEAM, DK> qp(S, d, w, a);
       QPResult r = qp.solve();
       o.qp_solves++; o.admm_iters += r.iters; o.last_status = r.status;
       if (r.status == 1 || r.status == 2) {
@@ -170,7 +170,7 @@ struct SqpSolver {
             sync();
             QPArgs a;
             a.prm = prm; a.Jg = Jg; a.pi = pi; a.kd = kd; a.use_pen = 1; a.closest = 0;
-            QPSolver<TEAM> qp(S, st, w, a);
+            QPSolver<TEAM, DK> qp(S, st, w, a);
             QPResult r = qp.solve();
             o.qp_solves++; o.admm_iters += r.iters; o.last_status = r.status;
             if (r.status == 1 || r.status == 2) {  // prob.py:197-205

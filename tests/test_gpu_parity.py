@@ -177,3 +177,28 @@ def test_batch_properties_at_scale(engines):
     out2 = eng.solve_batch(params[perm], x0[perm], s)
     assert np.array_equal(out2["x"].cpu().numpy(), x[perm])
     assert np.array_equal(out2["verdict"].cpu().numpy(), verdict[perm])
+
+
+def test_dense_register_path_matches_generic_path(engines):
+    """The two-warp register-resident ADMM loop (sco_qp_dense.inl) against the generic shared-memory
+    loop on the same QPs: same status, same iteration count, x to 1e-9; and the same SQP outcome."""
+    from sco_py_b200.engine import make_settings
+    eng, st, params, x0 = engines["qcqp"]
+    assert eng.team == 64
+    B = x0.shape[0]
+    f, J, b, _ = eng.convexify(params, x0)
+    for kdup, pi, delta in [(1, 1.0, 1.0), (4, 100.0, 0.01), (9, 1e4, 3e-5)]:
+        kw = dict(J=J, b=b, lbx=x0 - delta, ubx=x0 + delta, pi=np.full(B, pi), kdup=np.full(B, kdup, np.int32))
+        xa, sa, ia = eng.qp_solve(params, _settings(), **kw)
+        xb, sb, ib = eng.qp_solve(params, _settings(force_generic=1), **kw)
+        assert np.array_equal(sa.cpu().numpy(), sb.cpu().numpy())
+        assert np.array_equal(ia.cpu().numpy(), ib.cpu().numpy())
+        assert np.abs(xa.cpu().numpy() - xb.cpu().numpy()).max() <= 1e-9
+    _, p2, x2 = W.gen_batch("qcqp", 64)
+    a = eng.solve_batch(p2, x2, _settings())
+    g = eng.solve_batch(p2, x2, _settings(force_generic=1))
+    va, vg = a["verdict"].cpu().numpy(), g["verdict"].cpu().numpy()
+    assert (va == vg).mean() >= 0.98
+    same = va == vg
+    dx = np.abs(a["x"].cpu().numpy() - g["x"].cpu().numpy()).max(axis=1)
+    assert np.quantile(dx[same], 0.9) <= 1e-4
