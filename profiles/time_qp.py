@@ -20,3 +20,7 @@ for force in (0, 1):
     loop, chk, setup = xq[:, 0], xq[:, 1], xq[:, 2]
     print("force_generic=%d B=%d iters mean %.0f | cycles/iter (loop incl. checks) %.0f | check cycles per check %.0f | checks share %.1f%% | setup cycles %.0f" % (
         force, B, it.mean(), (loop / it).mean(), (chk / np.maximum(it // 25, 1)).mean(), 100 * chk.sum() / loop.sum(), setup.mean()))
+    if not force:
+        nchk = np.maximum(it // 25, 1)
+        print("   test stages (cycles per test): publish+barrier %.0f | mat-vecs+residuals %.0f | warp reductions %.0f | exchange %.0f | decision %.0f" % tuple(
+            (xq[:, 3 + k] / nchk).mean() for k in range(5)))

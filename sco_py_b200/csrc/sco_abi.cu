@@ -95,7 +95,7 @@ static void build_layout(DevStruct &S, int team) {
   L.msk = take((mp + 1) / 2);
   L.stage = take(std::max((team / 32) * S.stage_per_warp, 100));
   if (S.dense_kind) {
-    L.Ph = take(n * n); L.fbuf = take(2 * FBUF_LD + 64 + 256); L.Kd = take(n * mp);
+    L.Ph = take(n * n); L.fbuf = take(2 * FBUF_LD + 64); L.Kd = take(n * mp);
   } else {
     L.Ph = L.fbuf = L.Kd = 0;
   }

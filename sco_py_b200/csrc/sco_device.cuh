@@ -161,6 +161,25 @@ struct Team {
   }
 };
 
+// explicit shared-window accesses (32-bit addresses from __cvta_generic_to_shared)
+__device__ __forceinline__ double2 lds_v2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+// warp-wide maximum of non-negative doubles: their bit patterns order like unsigned integers, so
+// two redux.sync (high word, then low word among the lanes that hold the maximal high word) replace
+// the five shuffle rounds of a butterfly
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
+
 __device__ __forceinline__ double limit_scaling(double v) {
   v = v < OSQP_MIN_SCALING ? 1.0 : v;
   v = v > OSQP_MAX_SCALING ? OSQP_MAX_SCALING : v;

@@ -48,6 +48,14 @@ k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings
         stats[4 * b] = o.sqp_iters; stats[4 * b + 1] = o.qp_solves;
         stats[4 * b + 2] = o.admm_iters; stats[4 * b + 3] = o.last_status;
       }
+#ifdef SCO_TIMING
+      // diagnostic build only: the report slots carry the per-phase clock64() totals instead
+      if (merit) merit[b] = (double)o.cyc_total;
+      if (objective) objective[b] = (double)o.cyc_setup;
+      if (max_vio) max_vio[b] = (double)o.cyc_loop;
+      x_out[b * S.n] = (double)o.cyc_check;
+      x_out[b * S.n + 1] = (double)o.cyc_cvx;
+#endif
     }
     Team<TEAM>::sync();
   }
@@ -136,6 +144,7 @@ k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st
       iters[b] = r.iters;
 #ifdef SCO_TIMING
       xq[b * nq] = (double)r.cyc_loop; xq[b * nq + 1] = (double)r.cyc_check; xq[b * nq + 2] = (double)r.cyc_setup;
+      for (int k = 0; k < 5; k++) xq[b * nq + 3 + k] = (double)r.cyc_c[k];
 #endif
     }
     Team<TEAM>::sync();

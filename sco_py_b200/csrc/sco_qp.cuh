@@ -36,6 +36,7 @@ struct QPResult {
   double pri_res, dua_res;
 #ifdef SCO_TIMING
   long long cyc_loop, cyc_check, cyc_setup;  // clock64() ticks: ADMM loop (incl. checks), checks, setup
+  long long cyc_c[5];                        // stages of the termination test
 #endif
 };
 
@@ -682,6 +683,7 @@ struct QPSolver {
     res.status = 0; res.iters = 0; res.pri_res = 0.0; res.dua_res = 0.0;
 #ifdef SCO_TIMING
     res.cyc_check = 0;
+    for (int k = 0; k < 5; k++) res.cyc_c[k] = 0;
     res.cyc_setup = clock64() - t_begin;
     const long long t_loop = clock64();
 #endif

@@ -28,7 +28,6 @@ __device__ __forceinline__ int dense_loop(int &iter_out, bool &checked_out, QPRe
   const int ldj = (n & 1) ? n : n + 1;
   const Sh vb = w.fbuf;                       // 2 x VB_LD: (c[NP], wp[MP]) double-buffered
   const Sh xS = w.fbuf + 2 * FBUF_LD, yS = w.fbuf + 2 * FBUF_LD + 32;
-  const Sh prev = w.fbuf + 2 * FBUF_LD + 64;  // iterates of the iteration before a check: 4 x 64
   const Sh Ks = w.Kd;                         // K[j*m + i], n x m
 
   // ---- K = S^-1 J' into shared memory
@@ -63,8 +62,10 @@ __device__ __forceinline__ int dense_loop(int &iter_out, bool &checked_out, QPRe
   //   row lane     : u0=cpi*Ds  u1=sl  u2=bs    u3=hs      lo=kd*sl hi=up  Mi=Minv
   // Hinge rows and slack-bound rows always carry the scalar rho (their bounds are one-sided),
   // verified by dense_eligible(); their never-active clamps (-1e30 Ep, +1e30 Es) are dropped.
-  const double rho_u = rho, rhoi_u = 1.0 / rho;
-  double u0, u1, u2, u3, lo, hi, Mi = 0.0;
+  // Reciprocals of the scaling vectors for the termination test (r0, r1, r2):
+  //   variable lane: 1/Eb, 1/D, -        row lane: 1/Ep, 1/Es, 1/Ds       (0 on inactive lanes)
+  const double rho_u = rho, rhoi_u = 1.0 / rho, cinv = 1.0 / c;
+  double u0, u1, u2, u3, lo, hi, Mi = 0.0, r0, r1, r2 = 0.0;
   if (rowwarp) {
     u0 = isr ? cpi * w.Ds[lane] : 0.0;
     u1 = isr ? w.sl[lane] : 0.0;
@@ -73,6 +74,9 @@ __device__ __forceinline__ int dense_loop(int &iter_out, bool &checked_out, QPRe
     lo = kd * u1;
     hi = isr ? w.up[lane] : 0.0;
     Mi = isr ? w.Minv[3 * lane] : 0.0;
+    r0 = isr ? 1.0 / w.Ep[lane] : 0.0;
+    r1 = isr ? 1.0 / w.Es[lane] : 0.0;
+    r2 = isr ? 1.0 / w.Ds[lane] : 0.0;
   } else {
     u0 = isv ? w.qh[lane] : 0.0;
     u1 = isv ? w.bx[lane] : 0.0;
@@ -80,6 +84,8 @@ __device__ __forceinline__ int dense_loop(int &iter_out, bool &checked_out, QPRe
     u3 = 1.0 / u2;
     lo = isv ? w.lb[lane] : 0.0;
     hi = isv ? w.ub[lane] : 0.0;
+    r0 = isv ? 1.0 / w.Eb[lane] : 0.0;
+    r1 = isv ? 1.0 / w.D[lane] : 0.0;
   }
   // ---- iterates: (p0, z0, y0) = (x, zb, yb) or (-, zp, yp); row lanes also (s, zs, ys, g)
   double p0 = 0.0, z0 = 0.0, y0 = 0.0, s = 0.0, zs = 0.0, ys = 0.0;
@@ -87,34 +93,35 @@ __device__ __forceinline__ int dense_loop(int &iter_out, bool &checked_out, QPRe
   const double wp0 = -(rho_u * lo) * g;
   const int slot = rowwarp ? NP + lane : lane;           // this lane's entry of (c, wp)
   const bool publishes = rowwarp ? lane < MP : lane < NP;
-  for (int e = tid; e < 2 * FBUF_LD + 64 + 256; e += 64) vb[e] = 0.0;
+  for (int e = tid; e < 2 * FBUF_LD + 64; e += 64) vb[e] = 0.0;
   __syncthreads();
   if (publishes) vb[slot] = rowwarp ? wp0 : -u0;
-  int p = 0, iter, status = 0;
+  // 32-bit shared-window addresses: the loop below addresses shared memory through explicit
+  // ld.shared / st.shared so that nothing but the loads, the FMAs and the update is in its body
+  const uint32_t vb0 = (uint32_t)__cvta_generic_to_shared(vb.ptr());
+  const uint32_t vb1 = vb0 + 8u * FBUF_LD;
+  const uint32_t my_out = 8u * (uint32_t)slot;
+  const uint32_t my_chk = vb0 + 8u * (2 * FBUF_LD + (rowwarp ? 32 : 0) + lane);  // xS[lane] / yS[lane]
+  double pp0 = 0.0, py0 = 0.0, ps = 0.0, pys = 0.0;  // iterates before the last (checked) iteration
+  int iter = 0, status = 0;
   bool checked = false;
   const int max_iter = st.max_iter, chk = st.check_termination;
   int next_check = chk ? chk : max_iter + 1;
   __syncthreads();
 
-  for (iter = 1; iter <= max_iter; iter++) {
-    const bool want = iter == next_check;
-    if (want || iter == max_iter) {
-      // the infeasibility certificates need delta_x / delta_y of the checked iteration: remember
-      // the iterates it starts from (kept out of the update code below, which runs every iteration)
-      prev[tid] = p0; prev[64 + tid] = y0; prev[128 + tid] = s; prev[192 + tid] = ys;
-    }
-    const Sh vcur = vb + p * FBUF_LD;
+  // one ADMM iteration: reads (c, wp) at `vcur`, publishes this lane's new entry at `vnext`
+  auto iterate = [&](const uint32_t vcur, const uint32_t vnext) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
     for (int k = 0; k < NV / 4; k++) {
-      const double2 va = vcur.v2(2 * k), vc = vcur.v2(2 * k + 1);
+      const double2 va = lds_v2(vcur + 32u * k), vc = lds_v2(vcur + 32u * k + 16u);
       a0 = fma(Mr[4 * k], va.x, a0);
       a1 = fma(Mr[4 * k + 1], va.y, a1);
       a2 = fma(Mr[4 * k + 2], vc.x, a2);
       a3 = fma(Mr[4 * k + 3], vc.y, a3);
     }
     if (NV % 4) {
-      const double2 va = vcur.v2(NV / 2 - 1);
+      const double2 va = lds_v2(vcur + 8u * (NV - 2));
       a0 = fma(Mr[NV - 2], va.x, a0);
       a1 = fma(Mr[NV - 1], va.y, a1);
     }
@@ -126,133 +133,189 @@ __device__ __forceinline__ int dense_loop(int &iter_out, bool &checked_out, QPRe
       const double zt = acc + u1 * stil;
       const double sn = alpha * stil + oma * s;
       const double vs = alpha * (u2 * stil) + oma * zs;
-      const double zns = fmax(vs + ys * rhoi_u, 0.0);
-      const double dys = rho_u * (vs - zns);
-      ys += dys;
+      const double ts = vs + ys * rhoi_u;
+      const double zns = ts > 0.0 ? ts : 0.0;
+      ys += rho_u * (vs - zns);
       const double vv = alpha * zt + oma * z0;
-      const double zn = fmin(vv + y0 * rhoi_u, hi);
-      const double dyp = rho_u * (vv - zn);
-      y0 += dyp;
+      const double tz = vv + y0 * rhoi_u;
+      const double zn = tz < hi ? tz : hi;
+      y0 += rho_u * (vv - zn);
       s = sn;
       zs = zns;
       z0 = zn;
       const double wpen = rho_u * zn - y0;
-      const double r1 = sigma * sn - u0 + lo * wpen + u2 * (rho_u * zns - ys);
-      g = Mi * r1;
+      const double rr = sigma * sn - u0 + lo * wpen + u2 * (rho_u * zns - ys);
+      g = Mi * rr;
       out = kd * wpen - rho_u * (lo * g);
     } else {
       // x~ = acc ; x and box-row updates, then c for the next iteration
       const double xn = alpha * acc + oma * p0;
       const double vv = alpha * (u1 * acc) + oma * z0;
       const double zn = clampd(vv + y0 * u3, lo, hi);
-      const double dyb = u2 * (vv - zn);
-      y0 += dyb;
+      y0 += u2 * (vv - zn);
       p0 = xn;
       z0 = zn;
       out = sigma * xn - u0 + u1 * (u2 * zn - y0);
     }
-    p ^= 1;
-    if (publishes) vb[p * FBUF_LD + slot] = out;
-    checked = false;
-    if (want) {
-#ifdef SCO_TIMING
-      const long long tc0 = clock64();
-#endif
-      next_check += chk;
-      checked = true;
-      // ================= termination test (OSQP check_termination, unscaled residuals) =========
-      if (rowwarp) yS[lane] = kd * y0;
-      else xS[lane] = p0;
-      if (isr) { w.dss[lane] = s - prev[128 + tid]; w.dys[lane] = ys - prev[192 + tid]; w.dyp[lane] = y0 - prev[64 + tid]; }
-      if (isv) { w.dxv[lane] = p0 - prev[tid]; w.dyb[lane] = y0 - prev[64 + tid]; }
+    if (publishes) sts_f64(vnext + my_out, out);
+  };
+
+  int p = 0;
+  while (iter < max_iter) {
+    // ---- plain iterations up to (not including) the next checked / last one
+    const int seg_end = next_check < max_iter ? next_check : max_iter;
+    for (int i = iter + 1; i < seg_end; i++) {
+      iterate(p ? vb1 : vb0, p ? vb0 : vb1);
+      p ^= 1;
       __syncthreads();
-      double v[7] = {0, 0, 0, 0, 0, 0, 0};
-      if (isr) {
-        double ax = u1 * s;
-        for (int k = 0; k < n; k++) ax = fma(w.Js[lane * ldj + k], xS[k], ax);
-        double ei = 1.0 / w.Ep[lane];
-        v[0] = fabs((ax - z0) * ei); v[1] = fabs(z0 * ei); v[2] = fabs(ax * ei);
-        const double axs = u2 * s;
-        ei = 1.0 / w.Es[lane];
-        v[0] = fmax(v[0], fabs((axs - zs) * ei)); v[1] = fmax(v[1], fabs(zs * ei));
-        v[2] = fmax(v[2], fabs(axs * ei));
-        const double di = 1.0 / w.Ds[lane];
-        const double aty = lo * y0 + u2 * ys;
-        v[3] = fabs((u0 + aty) * di); v[4] = fabs(u0 * di); v[5] = fabs(aty * di);
-      }
-      if (isv) {
-        const double ax = u1 * p0, ei = 1.0 / w.Eb[lane];
-        v[0] = fabs((ax - z0) * ei); v[1] = fabs(z0 * ei); v[2] = fabs(ax * ei);
-        double px = 0.0, aty = 0.0;
-        for (int k = 0; k < n; k++) px = fma(w.Ph[k * n + lane], xS[k], px);
-        for (int i = 0; i < m_nl; i++) aty = fma(w.Js[i * ldj + lane], yS[i], aty);
-        aty += u1 * y0;
-        const double di = 1.0 / w.D[lane];
-        v[3] = fabs((u0 + px + aty) * di); v[4] = fabs(u0 * di);
-        v[5] = fabs(aty * di); v[6] = fabs(px * di);
-      }
-      Team<64>::reduce_max(v, w.red);
-      const double cinv = 1.0 / c;
-      const double pri_res = v[0], dua_res = cinv * v[3];
-      res.pri_res = pri_res;
-      res.dua_res = dua_res;
-      if (pri_res > OSQP_INFTY || dua_res > OSQP_INFTY) { status = -7; break; }
-      const double eps_p = st.eps_abs + st.eps_rel * fmax(v[1], v[2]);
-      const double eps_d = st.eps_abs + st.eps_rel * cinv * fmax(v[4], fmax(v[5], v[6]));
-      const bool prim_ok = pri_res < eps_p, dual_ok = dua_res < eps_d;
-      if (prim_ok && dual_ok) { status = 1; break; }
-      // first stage of the infeasibility certificates (lane-local); the second stage is rare and
-      // runs through the generic shared-memory code after spilling the iterates
-      bool stage2 = false;
-      if (!prim_ok) {
-        double nv[1] = {0.0}, lhs[1] = {0.0};
-        if (isr) {
-          const double lpl = w.lp[lane], usmax = OSQP_INFTY * w.Es[lane];
-          const double d1 = proj_dy(w.dyp[lane], lpl, hi), d2 = proj_dy(w.dys[lane], 0.0, usmax);
-          nv[0] = fmax(fabs(w.Ep[lane] * d1), fabs(w.Es[lane] * d2));
-          lhs[0] = kd * (hi * fmax(d1, 0.0) + lpl * fmin(d1, 0.0)) + usmax * fmax(d2, 0.0);
-        }
-        if (isv) {
-          const double d3 = proj_dy(w.dyb[lane], lo, hi);
-          nv[0] = fabs(w.Eb[lane] * d3);
-          lhs[0] = hi * fmax(d3, 0.0) + lo * fmin(d3, 0.0);
-        }
-        Team<64>::reduce_max(nv, w.red);
-        Team<64>::reduce_sum(lhs, w.red);
-        if (nv[0] > st.eps_prim_inf && lhs[0] < -st.eps_prim_inf * nv[0]) stage2 = true;
-      }
-      if (!dual_ok && !stage2) {
-        double nv[1] = {0.0}, qd[1] = {0.0};
-        if (isv) { nv[0] = fabs(w.D[lane] * w.dxv[lane]); qd[0] = u0 * w.dxv[lane]; }
-        if (isr) { nv[0] = fabs(w.Ds[lane] * w.dss[lane]); qd[0] = u0 * w.dss[lane]; }
-        Team<64>::reduce_max(nv, w.red);
-        Team<64>::reduce_sum(qd, w.red);
-        if (nv[0] > st.eps_dual_inf && qd[0] < -c * st.eps_dual_inf * nv[0]) stage2 = true;
-      }
-      if (stage2) {
-        if (isv) { w.x[lane] = p0; w.zb[lane] = z0; w.yb[lane] = y0; }
-        if (isr) { w.s[lane] = s; w.zs[lane] = zs; w.ys[lane] = ys; w.zp[lane] = z0; w.yp[lane] = y0; }
-        __syncthreads();
-        bool pinf = false, dinf = false;
-        if (!prim_ok) pinf = primal_infeasible(st.eps_prim_inf);
-        if (!dual_ok) dinf = dual_infeasible(st.eps_dual_inf);
-        if (pinf) { status = -3; break; }
-        if (dinf) { status = -4; break; }
-      }
-#ifdef SCO_TIMING
-      res.cyc_check += clock64() - tc0;
-#endif
     }
+    // ---- the checked (or last) iteration: the infeasibility certificates need delta_x / delta_y
+    pp0 = p0; py0 = y0; ps = s; pys = ys;
+    iterate(p ? vb1 : vb0, p ? vb0 : vb1);
+    p ^= 1;
+    iter = seg_end;
+    checked = false;
+    if (iter != next_check) { __syncthreads(); break; }
+    // ================= termination test (OSQP check_termination, unscaled residuals) ===========
+#ifdef SCO_TIMING
+    const long long tc0 = clock64();
+    long long tcs = tc0;
+#endif
+    next_check += chk;
+    checked = true;
+    sts_f64(my_chk, rowwarp ? kd * y0 : p0);
     __syncthreads();
+#ifdef SCO_TIMING
+    { const long long tq = clock64(); res.cyc_c[0] += tq - tcs; tcs = tq; }
+#endif
+    double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // 7 residual norms, |dy| and |dx| of the certificates
+    double sm2[2] = {0.0, 0.0};                  // their linear terms (sums)
+    if (rowwarp) {
+      // (J x)_i: compile-time trip count so the loads are issued back to back (a run-time loop makes
+      // every FMA wait for its own shared-memory round trip)
+      const Sh Jrow = w.Js + (isr ? lane : 0) * ldj;
+      double ax0 = 0.0, ax1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < NP; k += 2) {
+        const double2 xk = xS.v2(k >> 1);
+        if (k < n) ax0 = fma(Jrow[k], xk.x, ax0);
+        if (k + 1 < n) ax1 = fma(Jrow[k + 1], xk.y, ax1);
+      }
+      const double ax = (ax0 + ax1) + u1 * s;
+      v[0] = fabs((ax - z0) * r0); v[1] = fabs(z0 * r0); v[2] = fabs(ax * r0);
+      const double axs = u2 * s;
+      v[0] = fmax(v[0], fabs((axs - zs) * r1)); v[1] = fmax(v[1], fabs(zs * r1));
+      v[2] = fmax(v[2], fabs(axs * r1));
+      const double aty = lo * y0 + u2 * ys;
+      v[3] = fabs((u0 + aty) * r2); v[4] = fabs(u0 * r2); v[5] = fabs(aty * r2);
+      // first stage of the certificates (lane-local part)
+      const double Epl = isr ? w.Ep[lane] : 0.0, Esl = isr ? w.Es[lane] : 0.0, Dsl = isr ? w.Ds[lane] : 0.0;
+      const double lpl = -OSQP_INFTY * Epl, usmax = OSQP_INFTY * Esl;
+      const double d1 = isr ? proj_dy(y0 - py0, lpl, hi) : 0.0, d2 = isr ? proj_dy(ys - pys, 0.0, usmax) : 0.0;
+      v[7] = fmax(fabs(Epl * d1), fabs(Esl * d2));
+      sm2[0] = kd * (hi * fmax(d1, 0.0) + lpl * fmin(d1, 0.0)) + usmax * fmax(d2, 0.0);
+      const double dss = s - ps;
+      v[8] = fabs(Dsl * dss);
+      sm2[1] = u0 * dss;
+    } else {
+      const int col = isv ? lane : 0;
+      const double ax = u1 * p0;
+      v[0] = fabs((ax - z0) * r0); v[1] = fabs(z0 * r0); v[2] = fabs(ax * r0);
+      const Sh Pcol = w.Ph + col, Jcol = w.Js + col;
+      double px0 = 0.0, px1 = 0.0, at0 = 0.0, at1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < NP; k += 2) {
+        const double2 xk = xS.v2(k >> 1);
+        if (k < n) px0 = fma(Pcol[k * n], xk.x, px0);
+        if (k + 1 < n) px1 = fma(Pcol[(k + 1) * n], xk.y, px1);
+      }
+#pragma unroll
+      for (int i = 0; i < MP; i += 2) {
+        const double2 yi = yS.v2(i >> 1);
+        if (i < m_nl) at0 = fma(Jcol[i * ldj], yi.x, at0);
+        if (i + 1 < m_nl) at1 = fma(Jcol[(i + 1) * ldj], yi.y, at1);
+      }
+      const double px = px0 + px1, aty = (at0 + at1) + u1 * y0;
+      v[3] = fabs((u0 + px + aty) * r1); v[4] = fabs(u0 * r1);
+      v[5] = fabs(aty * r1); v[6] = fabs(px * r1);
+      const double Ebl = isv ? w.Eb[lane] : 0.0, Dl = isv ? w.D[lane] : 0.0;
+      const double d3 = isv ? proj_dy(y0 - py0, lo, hi) : 0.0;
+      v[7] = fabs(Ebl * d3);
+      sm2[0] = hi * fmax(d3, 0.0) + lo * fmin(d3, 0.0);
+      const double dx = p0 - pp0;
+      v[8] = fabs(Dl * dx);
+      sm2[1] = u0 * dx;
+    }
+#ifdef SCO_TIMING
+    { const long long tq = clock64(); res.cyc_c[1] += tq - tcs; tcs = tq; }
+#endif
+    // one combined team reduction: maxima through redux.sync on the (order-preserving) bit patterns
+#pragma unroll
+    for (int k = 0; k < 9; k++) v[k] = warp_max_nonneg(v[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sm2[0] += __shfl_xor_sync(0xffffffffu, sm2[0], o);
+      sm2[1] += __shfl_xor_sync(0xffffffffu, sm2[1], o);
+    }
+#ifdef SCO_TIMING
+    { const long long tq = clock64(); res.cyc_c[2] += tq - tcs; tcs = tq; }
+#endif
+    {
+      const int wi = rowwarp ? 0 : 1;
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) w.red[wi * 16 + k] = v[k];
+        w.red[wi * 16 + 9] = sm2[0];
+        w.red[wi * 16 + 10] = sm2[1];
+      }
+      __syncthreads();
+      const int wo = wi ^ 1;
+#pragma unroll
+      for (int k = 0; k < 9; k++) v[k] = fmax(v[k], w.red[wo * 16 + k]);
+      // fixed summation order (warp 0 + warp 1) so that both warps take the same decision
+      sm2[0] = w.red[9] + w.red[16 + 9];
+      sm2[1] = w.red[10] + w.red[16 + 10];
+    }
+#ifdef SCO_TIMING
+    { const long long tq = clock64(); res.cyc_c[3] += tq - tcs; tcs = tq; }
+#endif
+    const double pri_res = v[0], dua_res = cinv * v[3];
+    res.pri_res = pri_res;
+    res.dua_res = dua_res;
+    if (pri_res > OSQP_INFTY || dua_res > OSQP_INFTY) { status = -7; break; }
+    const double eps_p = st.eps_abs + st.eps_rel * fmax(v[1], v[2]);
+    const double eps_d = st.eps_abs + st.eps_rel * cinv * fmax(v[4], fmax(v[5], v[6]));
+    const bool prim_ok = pri_res < eps_p, dual_ok = dua_res < eps_d;
+    if (prim_ok && dual_ok) { status = 1; break; }
+    // the second stage of the infeasibility certificates is rare and runs through the generic
+    // shared-memory code after spilling the iterates
+    bool stage2 = false;
+    if (!prim_ok && v[7] > st.eps_prim_inf && sm2[0] < -st.eps_prim_inf * v[7]) stage2 = true;
+    if (!dual_ok && !stage2 && v[8] > st.eps_dual_inf && sm2[1] < -c * st.eps_dual_inf * v[8]) stage2 = true;
+    if (stage2) {
+      if (isv) { w.x[lane] = p0; w.zb[lane] = z0; w.yb[lane] = y0; w.dxv[lane] = p0 - pp0; w.dyb[lane] = y0 - py0; }
+      if (isr) {
+        w.s[lane] = s; w.zs[lane] = zs; w.ys[lane] = ys; w.zp[lane] = z0; w.yp[lane] = y0;
+        w.dss[lane] = s - ps; w.dys[lane] = ys - pys; w.dyp[lane] = y0 - py0;
+      }
+      __syncthreads();
+      bool pinf = false, dinf = false;
+      if (!prim_ok) pinf = primal_infeasible(st.eps_prim_inf);
+      if (!dual_ok) dinf = dual_infeasible(st.eps_dual_inf);
+      if (pinf) { status = -3; break; }
+      if (dinf) { status = -4; break; }
+    }
+#ifdef SCO_TIMING
+    { const long long tq = clock64(); res.cyc_c[4] += tq - tcs; res.cyc_check += tq - tc0; }
+#endif
   }
-  if (iter > max_iter) iter = max_iter;
-  // ---- hand the iterates back to the shared-memory arrays of the generic epilogue
+  // ---- hand the iterates (and the deltas of the last iteration) back to the shared-memory arrays
+  // of the generic epilogue
   __syncthreads();
-  if (isv) { w.x[lane] = p0; w.zb[lane] = z0; w.yb[lane] = y0; }
-  if (isr) { w.s[lane] = s; w.zs[lane] = zs; w.ys[lane] = ys; w.zp[lane] = z0; w.yp[lane] = y0; }
-  if (!checked) {
-    if (isr) { w.dss[lane] = s - prev[128 + tid]; w.dys[lane] = ys - prev[192 + tid]; w.dyp[lane] = y0 - prev[64 + tid]; }
-    if (isv) { w.dxv[lane] = p0 - prev[tid]; w.dyb[lane] = y0 - prev[64 + tid]; }
+  if (isv) { w.x[lane] = p0; w.zb[lane] = z0; w.yb[lane] = y0; w.dxv[lane] = p0 - pp0; w.dyb[lane] = y0 - py0; }
+  if (isr) {
+    w.s[lane] = s; w.zs[lane] = zs; w.ys[lane] = ys; w.zp[lane] = z0; w.yp[lane] = y0;
+    w.dss[lane] = s - ps; w.dys[lane] = ys - pys; w.dyp[lane] = y0 - py0;
   }
   __syncthreads();
   iter_out = iter;

@@ -16,6 +16,9 @@ struct SqpOut {
   int verdict;
   double merit, objective, max_vio;
   int sqp_iters, qp_solves, admm_iters, last_status;
+#ifdef SCO_TIMING
+  long long cyc_total, cyc_setup, cyc_loop, cyc_check, cyc_cvx;  // clock64() ticks per phase
+#endif
 };
 
 template <int TEAM, int DK>
@@ -119,6 +122,10 @@ struct SqpSolver {
     SqpOut o;
     o.verdict = 0; o.merit = 0; o.objective = 0; o.max_vio = 0;
     o.sqp_iters = 0; o.qp_solves = 0; o.admm_iters = 0; o.last_status = 0;
+#ifdef SCO_TIMING
+    o.cyc_setup = o.cyc_loop = o.cyc_check = o.cyc_cvx = 0;
+    const long long t_run = clock64();
+#endif
     for (int j = tid; j < n; j += TEAM) xc[j] = x0[j];
     sync();
     double mu = st.initial_penalty_coeff;
@@ -156,7 +163,13 @@ struct SqpSolver {
         while (!done_mm) {
           if (o.sqp_iters >= st.max_sqp_iters) { verdict = -1; finished = true; break; }
           o.sqp_iters++;
+#ifdef SCO_TIMING
+          const long long t_cvx = clock64();
+#endif
           convexify(mask_set);
+#ifdef SCO_TIMING
+          o.cyc_cvx += clock64() - t_cvx;
+#endif
           kd = st.duplicate_rows ? kd + 1.0 : 1.0;      // prob.py:508-509
           pi = st.compound_penalty ? pi * mu : mu;      // prob.py:424-426
           violation_sums(vs);
@@ -173,6 +186,9 @@ struct SqpSolver {
             QPSolver<TEAM, DK> qp(S, st, w, a);
             QPResult r = qp.solve();
             o.qp_solves++; o.admm_iters += r.iters; o.last_status = r.status;
+#ifdef SCO_TIMING
+            o.cyc_setup += r.cyc_setup; o.cyc_loop += r.cyc_loop; o.cyc_check += r.cyc_check;
+#endif
             if (r.status == 1 || r.status == 2) {  // prob.py:197-205
               for (int j = tid; j < n; j += TEAM) xc[j] = w.x[j];
               sync();
@@ -246,6 +262,9 @@ struct SqpSolver {
     o.objective = objective();
     o.merit = o.objective + mu * vs[0];
     o.max_vio = vs[1];
+#ifdef SCO_TIMING
+    o.cyc_total = clock64() - t_run;
+#endif
     return o;
   }
 };

@@ -23,10 +23,30 @@ cudaError_t configure(size_t bytes, int *occ) {
   if ((e = cudaFuncSetAttribute(k_convexify<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes))) return e;
   if ((e = cudaFuncSetAttribute(k_merit<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes))) return e;
 #endif
-  // the working sets are sized against the full 227 KB of shared memory per SM
+  // Shared-memory carve-out: first find the occupancy with the largest carve-out, then ask only for
+  // what that many CTAs need.  The rest of the 256 KB stays L1 cache: the kernels keep their stack
+  // frames and the structure's index arrays there, and with the maximal carve-out (28 KB of L1 left
+  // for 8+ warps) every such access was an L2 round trip.
   if ((e = cudaFuncSetAttribute(k_solve<T, DK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
-  if ((e = cudaFuncSetAttribute(k_qp<T, DK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_solve<T, DK>, T, bytes);
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_solve<T, DK>, T, bytes))) return e;
+  {
+    const size_t need = (size_t)(*occ > 0 ? *occ : 1) * (bytes + 1024);  // 1 KB per CTA is reserved by the driver
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    if ((e = cudaFuncSetAttribute(k_solve<T, DK>, cudaFuncAttributePreferredSharedMemoryCarveout, pct))) return e;
+    if ((e = cudaFuncSetAttribute(k_qp<T, DK>, cudaFuncAttributePreferredSharedMemoryCarveout, pct))) return e;
+#if SCO_DK == 0
+    if ((e = cudaFuncSetAttribute(k_convexify<T>, cudaFuncAttributePreferredSharedMemoryCarveout, pct))) return e;
+    if ((e = cudaFuncSetAttribute(k_merit<T>, cudaFuncAttributePreferredSharedMemoryCarveout, pct))) return e;
+#endif
+    int occ2 = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_solve<T, DK>, T, bytes))) return e;
+    if (occ2 < *occ) {  // the hint cost occupancy: go back to the maximal carve-out
+      if ((e = cudaFuncSetAttribute(k_solve<T, DK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
+      if ((e = cudaFuncSetAttribute(k_qp<T, DK>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))) return e;
+    }
+  }
+  return cudaSuccess;
 }
 void solve(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, const DevSettings &d,
            const SolveArgs &a) {
