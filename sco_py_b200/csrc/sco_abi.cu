@@ -73,7 +73,10 @@ static DevField cvt(const sco_field &f) {
 
 static void build_layout(DevStruct &S, int team) {
   Layout &L = S.L;
-  int off = 0;
+  // dense kinds: the two-warp solve owns a compile-time region at the start of dynamic shared memory
+  static const int dense_words[5] = {0, DenseL<8, 6>::total, DenseL<12, 16>::total, DenseL<20, 30>::total,
+                                     DenseL<32, 32>::total};
+  int off = dense_words[S.dense_kind];
   auto take = [&](int cnt) {
     int o = off;
     off += (cnt + 1) & ~1;
@@ -94,11 +97,6 @@ static void build_layout(DevStruct &S, int team) {
   L.red = take(8 * 16);
   L.msk = take((mp + 1) / 2);
   L.stage = take(std::max((team / 32) * S.stage_per_warp, 100));
-  if (S.dense_kind) {
-    L.Ph = take(n * n); L.fbuf = take(2 * FBUF_LD + 64); L.Kd = take(n * mp);
-  } else {
-    L.Ph = L.fbuf = L.Kd = 0;
-  }
   L.total = off;
 }
 

@@ -19,7 +19,6 @@
 #define OSQP_RHO_EQ_OVER_RHO_INEQ 1e3
 #define OSQP_RHO_TOL 1e-4
 
-#define FBUF_LD 66  // (c, wp) exchange vector: up to 32 + 32 entries + pad, even (16-byte aligned rows)
 
 struct DevField {
   long long off;
@@ -52,15 +51,46 @@ struct Layout {
   int red;    // reduction scratch: 8 warps * 8 values
   int msk;    // m_nl uint32 (counted in doubles, rounded up)
   int stage;  // per-warp staging buffers for family evaluation
-  // dense fast path (sco_qp_dense.cuh): scaled P, exchange buffers c (double-buffered), wp, x~
-  int Ph, fbuf, Kd;  // fbuf: (c, wp) double-buffered [2][FBUF_LD] + x[32] + kd*y[32] ; Kd: K = S^-1 J' (n x m)
   int total;  // doubles
+};
+
+// compile-time shared-memory layout (offsets in doubles, from the start of dynamic shared memory) of
+// the dense two-warp QP solve, sco_dense.cuh
+template <int NP, int MP>
+struct DenseL {
+  static constexpr int ev(int x) { return (x + 1) & ~1; }
+  static constexpr int LDJ = NP | 1;  // odd row stride: lane i reading J[i][k] is conflict-free
+  static constexpr int NV = NP + MP;
+  static constexpr int VLD = ev(NV) + 2;  // last slot = dump for the lanes that own no entry
+  static constexpr int NE = ev(NP), ME = ev(MP);
+  // matrices
+  static constexpr int Js = 0;                      // scaled, masked Jacobian  MP x LDJ
+  static constexpr int Si = Js + ev(MP * LDJ);      // Psym -> S -> S^-1        NP x NP
+  static constexpr int Ph = Si + ev(NP * NP);       // c D Psym D               NP x NP
+  static constexpr int Ks = Ph + ev(NP * NP);       // K = S^-1 J'              NP x MP
+  // exchange buffers
+  static constexpr int Vb = Ks + ev(NP * MP);       // (c, wp), double-buffered  2 x VLD
+  static constexpr int Xs = Vb + 2 * VLD;           // x of every variable (termination test)  32
+  static constexpr int Ys = Xs + 32;                // kd*y of every penalty row                32
+  static constexpr int Red = Ys + 32;               // two warps x 16 partial results
+  static constexpr int D = Red + 32;                // column scaling of the variables (32)
+  static constexpr int t1 = D + 32;                 // scratch per variable (32)
+  static constexpr int dg = t1 + 32;                // sigma + rho_j bx_j^2 (32)
+  static constexpr int cf = dg + 32;                // Schur coefficient per row (32)
+  // lane constants, [warp][k][lane]: 0 u0, 1 u1, 2 u2, 3 lo, 4 hi, 5 r0, 6 r1, 7 r2, 8 e0, 9 e1, 10 e2, 11 rho_j
+  static constexpr int LA = cf + 32;
+  static constexpr int NLA = 12;
+  // iterates handed to the rare paths (certificates, max_iter epilogue): 5 per variable, 8 per row
+  static constexpr int Sp = LA + 2 * NLA * 32;
+  // scalars: 0 eps_abs, 1 eps_rel, 2 eps_prim_inf, 3 eps_dual_inf, 4 c, 5 1/c, 6 c*pi, 7 rho, 8 kd
+  static constexpr int Sc = Sp + 13 * 32;
+  static constexpr int total = Sc + 16;
 };
 
 struct DevStruct {
   int n, m_lin, nnz_lin, n_blocks, n_groups, m_nl, n_slack, jnnz, n_q, nsl;
   int sjnnz;           // padded Jacobian entries in shared memory
-  int dense_kind;      // != 0: register-resident dense ADMM loop (sco_qp_dense.cuh), index into its size table
+  int dense_kind;      // != 0: two-warp dense solve (sco_dense.cuh), index into its size table
   int stage_per_warp;  // doubles
   long long stride;
   DevField Q, q, c, lin_l, lin_u;
@@ -199,7 +229,6 @@ struct QPW {
   Sh red;
   ShU32 msk;
   Sh stage;
-  Sh Ph, fbuf, Kd;
   Sh xc;  // current SQP iterate, n doubles appended after the layout
 
   __device__ __forceinline__ void bind(const Layout &L) {
@@ -217,7 +246,6 @@ struct QPW {
     red = Sh{L.red};
     msk = ShU32{L.msk};
     stage = Sh{L.stage};
-    Ph = Sh{L.Ph}; fbuf = Sh{L.fbuf}; Kd = Sh{L.Kd};
     xc = Sh{L.total};
   }
 };

@@ -64,6 +64,8 @@ __device__ __forceinline__ double proj_dy(double dy, double l, double u) {
   return dy;
 }
 
+#include "sco_dense.cuh"
+
 template <int TEAM, int DK>
 struct QPSolver {
   const DevStruct &S;
@@ -287,7 +289,6 @@ struct QPSolver {
       const int i = e / n, j = e % n;
       const double pv = reload ? psym(i, j) : w.Sm[e];
       double v = c * w.D[i] * pv * w.D[j];
-      if (S.dense_kind) w.Ph[e] = v;
       if (i == j) v += sigma + w.rb[j] * w.bx[j] * w.bx[j];
       w.Sm[e] = v;
     }
@@ -660,18 +661,17 @@ struct QPSolver {
     return status;
   }
 
-#include "sco_qp_dense.inl"
-
-  // the dense loop treats rho of the penalty rows and of the slack-bound rows as the scalar rho
-  __device__ bool dense_eligible() {
-    double bad[1] = {0.0};
-    for (int i = tid; i < m_nl; i += TEAM)
-      if (w.rp[i] != rho || w.rs[i] != rho || S.row_eq[i]) bad[0] = 1.0;
-    Team<TEAM>::reduce_max(bad, w.red);
-    return bad[0] == 0.0;
-  }
-
   __device__ __noinline__ QPResult solve() {
+    // dense hinge-only structures: the specialised two-warp solve (same iteration, sco_dense.cuh).
+    // The size table is kept in sync with sco_create (sco_abi.cu).
+    if constexpr (TEAM == 64 && DK != 0) {
+      if (!st.force_generic && !st.adaptive_rho && a.use_pen) {
+        if constexpr (DK == 1) return dense_qp_solve<8, 6>(S, st, w, a);
+        else if constexpr (DK == 2) return dense_qp_solve<12, 16>(S, st, w, a);
+        else if constexpr (DK == 3) return dense_qp_solve<20, 30>(S, st, w, a);
+        else return dense_qp_solve<32, 32>(S, st, w, a);
+      }
+    }
 #ifdef SCO_TIMING
     const long long t_begin = clock64();
 #endif
@@ -689,18 +689,7 @@ struct QPSolver {
 #endif
     int iter = 0, status = 0;
     bool checked = false;
-    bool dense = false;
-    if constexpr (TEAM == 64 && DK != 0) {
-      if (!st.force_generic && !st.adaptive_rho && a.use_pen && dense_eligible()) {
-        dense = true;
-        // keep in sync with the size table in sco_create (sco_abi.cu)
-        if constexpr (DK == 1) status = dense_loop<8, 6>(iter, checked, res);
-        else if constexpr (DK == 2) status = dense_loop<12, 16>(iter, checked, res);
-        else if constexpr (DK == 3) status = dense_loop<20, 30>(iter, checked, res);
-        else status = dense_loop<32, 32>(iter, checked, res);
-      }
-    }
-    if (!dense) status = generic_loop(iter, checked, res);
+    status = generic_loop(iter, checked, res);
 #ifdef SCO_TIMING
     res.cyc_loop = clock64() - t_loop;
 #endif
