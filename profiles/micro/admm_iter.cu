@@ -14,8 +14,18 @@ __device__ __forceinline__ double clampd(double v, double lo, double hi) { v = v
 struct Consts { double sigma, alpha, rho, kd; };
 
 // ---------------------------------------------------------------- variant 0
-__global__ void __maxnreg__(255)
-k_v0(const double *M, double *out, long long *cyc, int iters, Consts cs) {
+__device__ __forceinline__ double relu_bits(double v) {  // max(v, 0) through the sign bit
+  const int hi = __double2hiint(v), m = ~(hi >> 31);
+  return __hiloint2double(hi & m, __double2loint(v) & m);
+}
+template <int FAST>
+__device__ __forceinline__ void v0_body(const double *M, double *out, long long *cyc, int iters, Consts cs);
+__global__ void __maxnreg__(255) k_v0(const double *M, double *out, long long *cyc, int iters, Consts cs) { v0_body<0>(M, out, cyc, iters, cs); }
+__global__ void __maxnreg__(168) k_v0_168(const double *M, double *out, long long *cyc, int iters, Consts cs) { v0_body<0>(M, out, cyc, iters, cs); }
+__global__ void __maxnreg__(255) k_v0f(const double *M, double *out, long long *cyc, int iters, Consts cs) { v0_body<1>(M, out, cyc, iters, cs); }
+__global__ void __maxnreg__(168) k_v0f_168(const double *M, double *out, long long *cyc, int iters, Consts cs) { v0_body<1>(M, out, cyc, iters, cs); }
+template <int FAST>
+__device__ __forceinline__ void v0_body(const double *M, double *out, long long *cyc, int iters, Consts cs) {
   __shared__ __align__(16) double vb[2][NV + 2];
   const int tid = threadIdx.x, lane = tid & 31;
   const bool rowwarp = tid < 32;
@@ -46,7 +56,30 @@ k_v0(const double *M, double *out, long long *cyc, int iters, Consts cs) {
     { const double2 va = vc[NV / 2 - 1]; a0 = fma(Mr[NV - 2], va.x, a0); a1 = fma(Mr[NV - 1], va.y, a1); }
     const double acc = (a0 + a1) + (a2 + a3);
     double o;
-    if (rowwarp) {
+    if (FAST && rowwarp) {
+      // re-associated: y' = rho (t - z'), rho z' - y' = rho (2 z' - t); exact-arithmetic identities
+      const double stil = g - u3 * acc;
+      const double sn = alpha * stil + oma * s;
+      const double ts = (alpha * u2) * stil + (oma * zs + ys * rhoi);
+      const double zns = relu_bits(ts);
+      ys = rho * (ts - zns);
+      const double zt = acc + u1 * stil;
+      const double tz = alpha * zt + (oma * z0 + y0 * rhoi);
+      const double zn = tz < hi ? tz : hi;
+      y0 = rho * (tz - zn);
+      s = sn; zs = zns; z0 = zn;
+      const double wpen = rho * (2.0 * zn - tz);
+      const double r1 = (sigma * sn - u0) + u2 * (rho * (2.0 * zns - ts)) + lo * wpen;
+      g = Mi * r1;
+      o = kd * wpen - (rho * lo) * g;
+    } else if (FAST) {
+      const double xn = alpha * acc + oma * p0;
+      const double tz = (alpha * u1) * acc + (oma * z0 + y0 * u3);
+      const double zn = clampd(tz, lo, hi);
+      y0 = rho * (tz - zn);
+      p0 = xn; z0 = zn;
+      o = (sigma * xn - u0) + (u1 * rho) * (2.0 * zn - tz);
+    } else if (rowwarp) {
       const double stil = g - u3 * acc, zt = acc + u1 * stil, sn = alpha * stil + oma * s;
       const double vs = alpha * (u2 * stil) + oma * zs, zns = fmax(vs + ys * rhoi, 0.0);
       ys += rho * (vs - zns);
@@ -176,7 +209,8 @@ int main() {
   cudaMemcpy(dM, hM, NV * NV * 8, cudaMemcpyHostToDevice);
   Consts cs = {5e-10, 1.6, 0.1, 3.0};
   run("v0 2 warps full rows", k_v0, 64, dM, out, cyc, cs);
-  run("v1 4 warps half rows dup", k_v1<0>, 128, dM, out, cyc, cs);
-  run("v2 4 warps half rows even", k_v1<1>, 128, dM, out, cyc, cs);
+  run("v0 maxnreg 168", k_v0_168, 64, dM, out, cyc, cs);
+  run("v0 fast update", k_v0f, 64, dM, out, cyc, cs);
+  run("v0 fast update maxnreg 168", k_v0f_168, 64, dM, out, cyc, cs);
   return 0;
 }

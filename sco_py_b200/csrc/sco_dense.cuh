@@ -33,6 +33,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+// max(v, 0) through the sign bit (integer pipe; a double compare-and-select is four times the latency)
+__device__ __forceinline__ double relu_bits(double v) {
+  const int hi = __double2hiint(v), msk = ~(hi >> 31);
+  return __hiloint2double(hi & msk, __double2loint(v) & msk);
+}
 // maximum of two non-negative doubles (3 instructions; fmax() costs 7 with its NaN fix-up)
 __device__ __forceinline__ double max_nn(double a, double b) { return a > b ? a : b; }
 
@@ -548,11 +553,15 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
   }
   // ================================================================== K = S^-1 J'  (Ks[j*MP + i])
   for (int j = half; j < n; j += 2) {
-    if (lane < m) {
-      double acc = 0.0;
+    if (lane < MP) {  // padded rows (lane >= m) hold zeros in Js, so their K entries are exact zeros
+      double a0 = 0.0, a1 = 0.0;
       const uint32_t sj = sb + 8u * (DL::Si + j), jr = sb + 8u * (DL::Js + lane * LDJ);
-      for (int k = 0; k < NP; k++) acc = fma(lds_f64(sj + 8u * (k * NP)), lds_f64(jr + 8u * k), acc);
-      sts_f64(sb + 8u * (DL::Ks + j * MP + lane), acc);
+#pragma unroll 2
+      for (int k = 0; k < NP; k += 2) {
+        a0 = fma(lds_f64(sj + 8u * (k * NP)), lds_f64(jr + 8u * k), a0);
+        if (k + 1 < NP) a1 = fma(lds_f64(sj + 8u * ((k + 1) * NP)), lds_f64(jr + 8u * (k + 1)), a1);
+      }
+      sts_f64(sb + 8u * (DL::Ks + j * MP + lane), a0 + a1);
     }
   }
   // zero the exchange buffers meanwhile
@@ -563,13 +572,19 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
   if (rowwarp) {
 #pragma unroll
     for (int k = 0; k < NP; k++) Mr[k] = (act && k < n) ? lds_f64(sb + 8u * (DL::Ks + k * MP + lane)) : 0.0;
-    const uint32_t jr = sb + 8u * (DL::Js + lane * LDJ);
+    // G row: all MP accumulators in flight, one pass over k (K rows are read as broadcast 128-bit words)
+    const uint32_t jr = sb + 8u * (DL::Js + (act ? lane : 0) * LDJ);
 #pragma unroll
-    for (int l = 0; l < MP; l++) {
-      double acc = 0.0;
-      if (act && l < m)
-        for (int k = 0; k < n; k++) acc = fma(lds_f64(jr + 8u * k), lds_f64(sb + 8u * (DL::Ks + k * MP + l)), acc);
-      Mr[NP + l] = acc;
+    for (int l = 0; l < MP; l++) Mr[NP + l] = 0.0;
+    for (int k = 0; k < n; k++) {
+      const double jv = act ? lds_f64(jr + 8u * k) : 0.0;
+      const uint32_t kr = sb + 8u * (DL::Ks + k * MP);
+#pragma unroll
+      for (int l = 0; l < MP; l += 2) {
+        const double2 kk = lds_v2(kr + 8u * l);
+        Mr[NP + l] = fma(jv, kk.x, Mr[NP + l]);
+        Mr[NP + l + 1] = fma(jv, kk.y, Mr[NP + l + 1]);
+      }
     }
   } else {
 #pragma unroll
@@ -618,35 +633,36 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
     }
     const double acc = (a0 + a1) + (a2 + a3);
     double out;
+    // The updates are those of the generic loop (sco_qp.cuh generic_loop P1..P4) with the exact
+    // identities  y+ = y + rho (v - z+) = rho (t - z+),  rho z+ - y+ = rho (2 z+ - t),  t = v + y / rho,
+    // which shorten the dependent chain behind the dot product from 16 to 10 FP64 operations.
     if (rowwarp) {
       // t = acc ; slack and penalty-row updates, then wp for the next iteration
       const double stil = g - u3 * acc;
-      const double zt = acc + u1 * stil;
       const double sn = alpha * stil + oma * X.s;
-      const double vs = alpha * (u2 * stil) + oma * X.zs;
-      const double ts = vs + X.ys * rhoi;
-      const double zns = ts > 0.0 ? ts : 0.0;
-      X.ys += rho * (vs - zns);
-      const double vv = alpha * zt + oma * X.z0;
-      const double tz = vv + X.y0 * rhoi;
+      const double ts = (alpha * u2) * stil + (oma * X.zs + X.ys * rhoi);
+      const double zns = relu_bits(ts);
+      X.ys = rho * (ts - zns);
+      const double zt = acc + u1 * stil;
+      const double tz = alpha * zt + (oma * X.z0 + X.y0 * rhoi);
       const double zn = tz < hi ? tz : hi;
-      X.y0 += rho * (vv - zn);
+      X.y0 = rho * (tz - zn);
       X.s = sn;
       X.zs = zns;
       X.z0 = zn;
-      const double wpen = rho * zn - X.y0;
-      const double rr = sigma * sn - u0 + lo * wpen + u2 * (rho * zns - X.ys);
+      const double wpen = rho * (2.0 * zn - tz);
+      const double rr = (sigma * sn - u0) + u2 * (rho * (2.0 * zns - ts)) + lo * wpen;
       g = Mi * rr;
-      out = kd * wpen - rho * (lo * g);
+      out = kd * wpen - (rho * lo) * g;
     } else {
       // x~ = acc ; x and box-row updates, then c for the next iteration
       const double xn = alpha * acc + oma * X.p0;
-      const double vv = alpha * (u1 * acc) + oma * X.z0;
-      const double zn = clampd(vv + X.y0 * u3, lo, hi);
-      X.y0 += u2 * (vv - zn);
+      const double tz = (alpha * u1) * acc + (oma * X.z0 + X.y0 * u3);
+      const double zn = clampd(tz, lo, hi);
+      X.y0 = u2 * (tz - zn);
       X.p0 = xn;
       X.z0 = zn;
-      out = sigma * xn - u0 + u1 * (u2 * zn - X.y0);
+      out = (sigma * xn - u0) + (u1 * u2) * (2.0 * zn - tz);
     }
     sts_f64(vnext + my_out, out);
   };
