@@ -125,6 +125,7 @@ def workload_config(args, per_gpu_batch):
              "arm": "C3 7-DOF arm T=20 (configs[2]), rng seeds 3000+i"}
     return {"workload": names[args.config], "batch_per_gpu": per_gpu_batch,
             "global_batch": per_gpu_batch * args.gpus, "parallelism": "problems sharded, dp%d" % args.gpus,
+            "pipelining": "steps (independent batches) round-robin over %d CUDA streams" % max(1, min(getattr(args, "streams", 1), 4)),
             "solver": "penalty_sqp, test_solver.py:15-25 hyper-parameters (mu0=1), OSQP eps_abs 1e-6 eps_rel 1e-9 "
                       "rho 0.1 fixed, reference quirks C-1..C-3 on",
             "l2": "inputs (%.2f GB of parameters per GPU) exceed the 126 MB L2; no flush needed"
@@ -262,50 +263,79 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- device-resident leg
-    out = None
-    for _ in range(args.warmup):
-        out = eng.solve_batch(d_params, d_x0, settings)
+    # ---- device-resident leg.  Steps are independent batches: they are pipelined over `--streams`
+    # CUDA streams (launch slots of the handle), so the tail of one launch -- a few long problems on
+    # a handful of SMs -- overlaps the next launch.  The timed region is still K whole steps.
+    n_streams = max(1, min(args.streams, 4))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    cur = torch.cuda.current_stream(dev)
+
+    def run_steps(count):
+        outs = []
+        for s_ in streams:
+            s_.wait_stream(cur)
+        for i in range(count):
+            outs.append(eng.solve_batch(d_params, d_x0, settings, stream=streams[i % n_streams]))
+        for s_ in streams:
+            cur.wait_stream(s_)
+        return outs
+
+    run_steps(args.warmup)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    stream = torch.cuda.current_stream(dev)
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        out = eng.solve_batch(d_params, d_x0, settings)
-    e1.record(stream)
+    e0.record(cur)
+    outs = run_steps(args.steps)
+    e1.record(cur)
     barrier()
     ms_total = reduce_max(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
+    out = outs[-1]
     verdict = out["verdict"].cpu().numpy()
     stats = out["stats"].cpu().numpy()
+    for o_ in outs[:-1]:
+        if not torch.equal(o_["verdict"], out["verdict"]) or not torch.equal(o_["x"], out["x"]):
+            raise SystemExit("bench.py: two steps over the same batch disagree")
     converged = reduce_sum(float((verdict == 1).sum()))
     value = converged * args.steps / (ms_total * 1e-3)
 
-    # ---- end-to-end leg: host buffers through the C ABI, copies inside the timed region
-    h_out = dict(x=torch.empty((B, st.n), dtype=torch.float64, pin_memory=True).numpy(),
-                 verdict=torch.empty(B, dtype=torch.int32, pin_memory=True).numpy(),
-                 merit=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
-                 objective=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
-                 max_vio=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
-                 stats=torch.empty((B, 4), dtype=torch.int32, pin_memory=True).numpy())
+    # ---- end-to-end leg: host buffers through the C ABI (sco_solve_batch_host_async), the H2D copy
+    # of every step's inputs and the D2H copy of its results inside the timed region, same pipelining
+    def host_out():
+        return dict(x=torch.empty((B, st.n), dtype=torch.float64, pin_memory=True).numpy(),
+                    verdict=torch.empty(B, dtype=torch.int32, pin_memory=True).numpy(),
+                    merit=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
+                    objective=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
+                    max_vio=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
+                    stats=torch.empty((B, 4), dtype=torch.int32, pin_memory=True).numpy())
+
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    eng.solve_batch_host(h_params.numpy(), h_x0.numpy(), settings, out=h_out)  # warm-up (allocations)
+    h_outs = [host_out() for _ in range(min(e2e_steps, n_streams))]
+
+    def run_e2e(count):
+        for i in range(count):
+            eng.solve_batch_host(h_params.numpy(), h_x0.numpy(), settings, out=h_outs[i % len(h_outs)],
+                                 stream=streams[i % n_streams])
+        for s_ in streams:
+            s_.synchronize()
+
+    run_e2e(1)  # warm-up (staging allocations)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.solve_batch_host(h_params.numpy(), h_x0.numpy(), settings, out=h_out)
+    run_e2e(e2e_steps)
     barrier()
     e2e_s = reduce_max(time.perf_counter() - t0)
+    h_out = h_outs[0]
     e2e_conv = reduce_sum(float((h_out["verdict"] == 1).sum()))
     e2e_value = e2e_conv * e2e_steps / e2e_s
     h2d = h_params.numel() * 8 + h_x0.numel() * 8
     d2h = sum(v.nbytes for v in h_out.values())
-    if not np.array_equal(h_out["verdict"], verdict) or not np.array_equal(h_out["x"], out["x"].cpu().numpy()):
-        raise SystemExit("bench.py: host-buffer path and device path disagree")
+    for ho in h_outs:
+        if not np.array_equal(ho["verdict"], verdict) or not np.array_equal(ho["x"], out["x"].cpu().numpy()):
+            raise SystemExit("bench.py: host-buffer path and device path disagree")
 
     if rank != 0:
         if world > 1:
@@ -395,7 +425,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="qcqp", choices=["qcqp", "point_robot", "arm"])
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the steps are pipelined over (1..4)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU sample (default: one per core)")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

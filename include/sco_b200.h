@@ -158,7 +158,17 @@ int sco_solve_batch(sco_handle *h, int64_t B, const double *d_params, const doub
                     const sco_settings *s, double *d_x_out, int32_t *d_verdict, double *d_merit,
                     double *d_objective, double *d_max_vio, int32_t *d_stats, void *stream);
 
-/* Same with HOST buffers (pinned or pageable): copies in, solves, copies out, synchronises. */
+/* Launches of one handle may be in flight on several streams at once (each owns one of four launch
+ * slots: work-queue counter + Jacobian scratch); calls on one handle must come from one host thread. */
+
+/* Same with HOST buffers: copies in, solves, copies out -- all enqueued on `stream`, no host
+ * synchronisation (pinned buffers make the copies asynchronous; the caller synchronises the stream
+ * before reading the outputs).  Up to four calls may be in flight (one staging set each). */
+int sco_solve_batch_host_async(sco_handle *h, int64_t B, const double *params, const double *x0,
+                               const sco_settings *s, double *x_out, int32_t *verdict, double *merit,
+                               double *objective, double *max_vio, int32_t *stats, void *stream);
+
+/* Same on the default stream, then synchronises (pinned or pageable buffers). */
 int sco_solve_batch_host(sco_handle *h, int64_t B, const double *params, const double *x0,
                          const sco_settings *s, double *x_out, int32_t *verdict, double *merit,
                          double *objective, double *max_vio, int32_t *stats);

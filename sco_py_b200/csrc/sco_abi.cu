@@ -42,14 +42,23 @@ struct sco_handle {
   size_t smem_bytes = 0;
   DevStruct S;
   std::vector<void *> dev_allocs;
-  double *Jscr = nullptr;
+  // Launch slots: every launch owns a work-queue counter and a Jacobian scratch area until it ends,
+  // so launches of one handle may be in flight on several streams at once (batches pipelined over
+  // streams hide the tail of a launch, where a few long problems keep a handful of SMs busy).
+  static const int NSLOT = 4;
+  double *Jscr[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
   size_t Jscr_ctas = 0;
-  unsigned long long *counter = nullptr;
-  // host-entry staging buffers (grow-only)
-  double *d_params = nullptr, *d_x0 = nullptr, *d_x = nullptr, *d_merit = nullptr, *d_obj = nullptr,
-         *d_vio = nullptr;
-  int *d_verdict = nullptr, *d_stats = nullptr;
-  long long cap_B = 0;
+  unsigned long long *counter = nullptr;  // NSLOT counters
+  cudaEvent_t slot_done[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned next_slot = 0;
+  // host-entry staging buffers, one set per slot (grow-only)
+  struct Staging {
+    double *params = nullptr, *x0 = nullptr, *x = nullptr, *merit = nullptr, *obj = nullptr, *vio = nullptr;
+    int *verdict = nullptr, *stats = nullptr;
+    long long cap_B = 0;
+    cudaEvent_t done = nullptr;
+  } stg[NSLOT];
+  unsigned next_stg = 0;
 };
 
 template <typename T>
@@ -322,8 +331,13 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
     h->occupancy = std::max(occ, 1);
   }
   h->Jscr_ctas = (size_t)h->sm_count * h->occupancy;
-  if (cudaMalloc(&h->Jscr, std::max<size_t>(h->Jscr_ctas * std::max(jnnz, 1), 1) * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&h->counter, sizeof(unsigned long long)) != cudaSuccess) {
+  bool ok = cudaMalloc(&h->counter, sco_handle::NSLOT * sizeof(unsigned long long)) == cudaSuccess;
+  for (int k = 0; k < sco_handle::NSLOT && ok; k++) {
+    ok = cudaMalloc(&h->Jscr[k], std::max<size_t>(h->Jscr_ctas * std::max(jnnz, 1), 1) * sizeof(double)) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->slot_done[k], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->stg[k].done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
     sco_destroy(h);
     return fail(SCO_ERR_CUDA, "cudaMalloc of scratch failed");
   }
@@ -335,9 +349,15 @@ extern "C" int sco_destroy(sco_handle *h) {
   if (!h) return SCO_OK;
   cudaSetDevice(h->device);
   for (void *p : h->dev_allocs) cudaFree(p);
-  cudaFree(h->Jscr); cudaFree(h->counter);
-  cudaFree(h->d_params); cudaFree(h->d_x0); cudaFree(h->d_x); cudaFree(h->d_merit); cudaFree(h->d_obj);
-  cudaFree(h->d_vio); cudaFree(h->d_verdict); cudaFree(h->d_stats);
+  cudaFree(h->counter);
+  for (int k = 0; k < sco_handle::NSLOT; k++) {
+    cudaFree(h->Jscr[k]);
+    if (h->slot_done[k]) cudaEventDestroy(h->slot_done[k]);
+    sco_handle::Staging &g = h->stg[k];
+    cudaFree(g.params); cudaFree(g.x0); cudaFree(g.x); cudaFree(g.merit); cudaFree(g.obj); cudaFree(g.vio);
+    cudaFree(g.verdict); cudaFree(g.stats);
+    if (g.done) cudaEventDestroy(g.done);
+  }
   delete h;
   return SCO_OK;
 }
@@ -358,12 +378,15 @@ extern "C" int sco_solve_batch(sco_handle *h, int64_t B, const double *d_params,
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   DevSettings d = to_dev(s);
-  CUDA_TRY(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+  const int slot = (int)(h->next_slot++ % sco_handle::NSLOT);
+  CUDA_TRY(cudaStreamWaitEvent(st, h->slot_done[slot], 0));  // the slot's previous launch (any stream)
+  CUDA_TRY(cudaMemsetAsync(h->counter + slot, 0, sizeof(unsigned long long), st));
   const long long grid = std::min<long long>(B, (long long)h->Jscr_ctas);
   SolveArgs a = {(long long)B, d_params, d_x0, d_x_out, d_verdict, d_merit, d_objective, d_max_vio, d_stats,
-                 h->Jscr, h->counter};
+                 h->Jscr[slot], h->counter + slot};
   h->ops->solve((unsigned)grid, h->smem_bytes, st, h->S, d, a);
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(h->slot_done[slot], st));
   return SCO_OK;
 }
 
@@ -375,35 +398,47 @@ static int grow(T **p, size_t count) {
   return 0;
 }
 
-extern "C" int sco_solve_batch_host(sco_handle *h, int64_t B, const double *params, const double *x0,
-                                    const sco_settings *s, double *x_out, int32_t *verdict,
-                                    double *merit, double *objective, double *max_vio,
-                                    int32_t *stats) {
+extern "C" int sco_solve_batch_host_async(sco_handle *h, int64_t B, const double *params, const double *x0,
+                                          const sco_settings *s, double *x_out, int32_t *verdict,
+                                          double *merit, double *objective, double *max_vio,
+                                          int32_t *stats, void *stream) {
   if (!h || !s || !params || !x0 || !x_out || !verdict) return fail(SCO_ERR_ARG, "null argument");
   if (B <= 0) return SCO_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   const int n = h->S.n;
-  if (B > h->cap_B) {
+  cudaStream_t st = (cudaStream_t)stream;
+  sco_handle::Staging &g = h->stg[h->next_stg++ % sco_handle::NSLOT];
+  if (B > g.cap_B) {
+    CUDA_TRY(cudaEventSynchronize(g.done));  // nothing in flight may still use the old buffers
     int rc = 0;
-    rc |= grow(&h->d_params, (size_t)B * h->S.stride); rc |= grow(&h->d_x0, (size_t)B * n);
-    rc |= grow(&h->d_x, (size_t)B * n); rc |= grow(&h->d_merit, (size_t)B); rc |= grow(&h->d_obj, (size_t)B);
-    rc |= grow(&h->d_vio, (size_t)B); rc |= grow(&h->d_verdict, (size_t)B); rc |= grow(&h->d_stats, (size_t)4 * B);
+    rc |= grow(&g.params, (size_t)B * h->S.stride); rc |= grow(&g.x0, (size_t)B * n);
+    rc |= grow(&g.x, (size_t)B * n); rc |= grow(&g.merit, (size_t)B); rc |= grow(&g.obj, (size_t)B);
+    rc |= grow(&g.vio, (size_t)B); rc |= grow(&g.verdict, (size_t)B); rc |= grow(&g.stats, (size_t)4 * B);
     if (rc) return SCO_ERR_CUDA;
-    h->cap_B = B;
+    g.cap_B = B;
   }
-  cudaStream_t st = 0;
-  CUDA_TRY(cudaMemcpyAsync(h->d_params, params, (size_t)B * h->S.stride * sizeof(double), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(h->d_x0, x0, (size_t)B * n * sizeof(double), cudaMemcpyHostToDevice, st));
-  int rc = sco_solve_batch(h, B, h->d_params, h->d_x0, s, h->d_x, h->d_verdict, h->d_merit, h->d_obj,
-                           h->d_vio, h->d_stats, st);
+  CUDA_TRY(cudaStreamWaitEvent(st, g.done, 0));
+  CUDA_TRY(cudaMemcpyAsync(g.params, params, (size_t)B * h->S.stride * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(g.x0, x0, (size_t)B * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = sco_solve_batch(h, B, g.params, g.x0, s, g.x, g.verdict, g.merit, g.obj, g.vio, g.stats, st);
   if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(x_out, h->d_x, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(verdict, h->d_verdict, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  if (merit) CUDA_TRY(cudaMemcpyAsync(merit, h->d_merit, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (objective) CUDA_TRY(cudaMemcpyAsync(objective, h->d_obj, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (max_vio) CUDA_TRY(cudaMemcpyAsync(max_vio, h->d_vio, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (stats) CUDA_TRY(cudaMemcpyAsync(stats, h->d_stats, (size_t)4 * B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaMemcpyAsync(x_out, g.x, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(verdict, g.verdict, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (merit) CUDA_TRY(cudaMemcpyAsync(merit, g.merit, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (objective) CUDA_TRY(cudaMemcpyAsync(objective, g.obj, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (max_vio) CUDA_TRY(cudaMemcpyAsync(max_vio, g.vio, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (stats) CUDA_TRY(cudaMemcpyAsync(stats, g.stats, (size_t)4 * B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(g.done, st));
+  return SCO_OK;
+}
+
+extern "C" int sco_solve_batch_host(sco_handle *h, int64_t B, const double *params, const double *x0,
+                                    const sco_settings *s, double *x_out, int32_t *verdict,
+                                    double *merit, double *objective, double *max_vio,
+                                    int32_t *stats) {
+  int rc = sco_solve_batch_host_async(h, B, params, x0, s, x_out, verdict, merit, objective, max_vio, stats, nullptr);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(0));
   return SCO_OK;
 }
 
@@ -417,7 +452,7 @@ extern "C" int sco_convexify(sco_handle *h, int64_t B, const double *d_params, c
   if (B <= 0) return SCO_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  ConvexifyArgs a = {(long long)B, d_params, d_x, d_f, d_J, d_b, d_obj, h->Jscr};
+  ConvexifyArgs a = {(long long)B, d_params, d_x, d_f, d_J, d_b, d_obj, h->Jscr[0]};
   h->gen_ops->convexify(stage_grid(h, B), h->smem_bytes, st, h->S, a);
   CUDA_TRY(cudaGetLastError());
   return SCO_OK;

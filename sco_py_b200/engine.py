@@ -3,6 +3,7 @@
 PyTorch is used only to own device memory and streams; every numerical step is a
 kernel of libsco_b200.so reached through ctypes.
 """
+import contextlib
 import ctypes
 
 import numpy as np
@@ -108,23 +109,26 @@ class Engine(object):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ------------------------------------------------------------------ hot path
-    def solve_batch(self, params, x0, settings):
-        """Device-resident solve.  Returns dict of torch tensors (x, verdict, merit, objective, max_vio, stats)."""
-        params, x0 = self._dev(params), self._dev(x0)
-        B = x0.shape[0]
-        x = torch.empty_like(x0)
-        verdict = torch.empty(B, dtype=torch.int32, device=self.device)
-        merit = torch.empty(B, dtype=torch.float64, device=self.device)
-        obj = torch.empty_like(merit)
-        vio = torch.empty_like(merit)
-        stats = torch.empty((B, 4), dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.sco_solve_batch(self.h, B, _ptr(params), _ptr(x0), ctypes.byref(settings),
-                                            _ptr(x), _ptr(verdict), _ptr(merit), _ptr(obj), _ptr(vio),
-                                            _ptr(stats), self._stream()))
+    def solve_batch(self, params, x0, settings, stream=None):
+        """Device-resident solve, enqueued on `stream` (default: torch's current stream).
+        Returns dict of torch tensors (x, verdict, merit, objective, max_vio, stats)."""
+        with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+            params, x0 = self._dev(params), self._dev(x0)
+            B = x0.shape[0]
+            x = torch.empty_like(x0)
+            verdict = torch.empty(B, dtype=torch.int32, device=self.device)
+            merit = torch.empty(B, dtype=torch.float64, device=self.device)
+            obj = torch.empty_like(merit)
+            vio = torch.empty_like(merit)
+            stats = torch.empty((B, 4), dtype=torch.int32, device=self.device)
+            _lib.check(self.lib.sco_solve_batch(self.h, B, _ptr(params), _ptr(x0), ctypes.byref(settings),
+                                                _ptr(x), _ptr(verdict), _ptr(merit), _ptr(obj), _ptr(vio),
+                                                _ptr(stats), self._stream()))
         return dict(x=x, verdict=verdict, merit=merit, objective=obj, max_vio=vio, stats=stats)
 
-    def solve_batch_host(self, params, x0, settings, out=None):
-        """Host buffers in, host buffers out (copies inside): the end-to-end entry."""
+    def solve_batch_host(self, params, x0, settings, out=None, stream=None):
+        """Host buffers in, host buffers out (copies inside): the end-to-end entry.  With `stream`
+        (a torch.cuda.Stream) everything is only enqueued there -- pinned buffers, caller synchronises."""
         params = np.ascontiguousarray(params, dtype=np.float64)
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         B = x0.shape[0]
@@ -132,6 +136,12 @@ class Engine(object):
             out = dict(x=np.empty_like(x0), verdict=np.empty(B, np.int32), merit=np.empty(B),
                        objective=np.empty(B), max_vio=np.empty(B), stats=np.empty((B, 4), np.int32))
         vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        if stream is not None:
+            _lib.check(self.lib.sco_solve_batch_host_async(
+                self.h, B, vp(params), vp(x0), ctypes.byref(settings), vp(out["x"]), vp(out["verdict"]),
+                vp(out["merit"]), vp(out["objective"]), vp(out["max_vio"]), vp(out["stats"]),
+                ctypes.c_void_p(stream.cuda_stream)))
+            return out
         _lib.check(self.lib.sco_solve_batch_host(self.h, B, vp(params), vp(x0), ctypes.byref(settings),
                                                  vp(out["x"]), vp(out["verdict"]), vp(out["merit"]),
                                                  vp(out["objective"]), vp(out["max_vio"]),
