@@ -13,7 +13,8 @@
  * every check_termination iterations, unscaling).  SURVEY.md Appendix B is the
  * spec followed.  Parity is pinned on the reference's own known-answer tests
  * (tests/sco_osqp/*.py run unmodified on top of this core through the
- * oracle/shims/osqp module -- see tests/test_oracle_reference_suite.py).
+ * oracle/shims/osqp module -- see tests/test_oracle.py) and on golden QPs captured
+ * at the reference's own call site (tests/golden/, oracle/gen_golden.py).
  * ADMM-iterate parity with upstream OSQP is NOT pinned.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
