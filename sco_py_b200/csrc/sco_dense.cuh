@@ -410,19 +410,35 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
   for (int it = 0; it < scaling; it++) {
     double e_row = 1.0, d_sl = 1.0, e_sl = 1.0, d_var = 1.0, e_box = 1.0;
     if (rowwarp) {
-      double rn = fabs(sl);
+      // all norms are maxima of absolute values: max_nn (3 instructions) on two independent chains
+      double rn = fabs(sl), rn2 = 0.0;
       const uint32_t jr = sb + 8u * (DL::Js + lane * LDJ);
-      for (int k = 0; k < NP; k++) rn = fmax(rn, fabs(lds_f64(jr + 8u * k)));
+#pragma unroll 4
+      for (int k = 0; k < NP; k += 2) {
+        rn = max_nn(rn, fabs(lds_f64(jr + 8u * k)));
+        if (k + 1 < NP) rn2 = max_nn(rn2, fabs(lds_f64(jr + 8u * (k + 1))));
+      }
+      rn = max_nn(rn, rn2);
       if (!act) rn = 0.0;
       e_row = 1.0 / sqrt(limit_scaling(rn));
       d_sl = 1.0 / sqrt(limit_scaling(fmax(fabs(sl), fabs(bs))));
       e_sl = 1.0 / sqrt(limit_scaling(fabs(bs)));
     } else {
-      double cp = 0.0, ca = fabs(bx);
+      double cp = 0.0, cp2 = 0.0, ca = fabs(bx), ca2 = 0.0;
       const uint32_t pc = sb + 8u * (DL::Si + lane), jc = sb + 8u * (DL::Js + lane), dd = sb + 8u * DL::D;
-      for (int i = 0; i < NP; i++) cp = fmax(cp, lds_f64(dd + 8u * i) * fabs(lds_f64(pc + 8u * (i * NP))));
-      cp = cp * c * D;
-      for (int i = 0; i < MP; i++) ca = fmax(ca, fabs(lds_f64(jc + 8u * (i * LDJ))));
+#pragma unroll 4
+      for (int i = 0; i < NP; i += 2) {
+        const double2 di = lds_v2(dd + 8u * i);
+        cp = max_nn(cp, di.x * fabs(lds_f64(pc + 8u * (i * NP))));
+        if (i + 1 < NP) cp2 = max_nn(cp2, di.y * fabs(lds_f64(pc + 8u * ((i + 1) * NP))));
+      }
+      cp = max_nn(cp, cp2) * c * D;
+#pragma unroll 4
+      for (int i = 0; i < MP; i += 2) {
+        ca = max_nn(ca, fabs(lds_f64(jc + 8u * (i * LDJ))));
+        if (i + 1 < MP) ca2 = max_nn(ca2, fabs(lds_f64(jc + 8u * ((i + 1) * LDJ))));
+      }
+      ca = max_nn(ca, ca2);
       if (!act) { cp = 0.0; ca = 0.0; }
       d_var = 1.0 / sqrt(limit_scaling(fmax(cp, ca)));
       e_box = 1.0 / sqrt(limit_scaling(fabs(bx)));
@@ -452,10 +468,15 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
       if (act) vm = fabs(c * pi) * Ds;
     } else {
       if (act) {
-        double cp = 0.0;
+        double cp = 0.0, cp2 = 0.0;
         const uint32_t pc = sb + 8u * (DL::Si + lane), dd = sb + 8u * DL::D;
-        for (int i = 0; i < NP; i++) cp = fmax(cp, lds_f64(dd + 8u * i) * fabs(lds_f64(pc + 8u * (i * NP))));
-        vs = cp * c * D;
+#pragma unroll 4
+        for (int i = 0; i < NP; i += 2) {
+          const double2 di = lds_v2(dd + 8u * i);
+          cp = max_nn(cp, di.x * fabs(lds_f64(pc + 8u * (i * NP))));
+          if (i + 1 < NP) cp2 = max_nn(cp2, di.y * fabs(lds_f64(pc + 8u * ((i + 1) * NP))));
+        }
+        vs = max_nn(cp, cp2) * c * D;
         vm = fabs(qh);
       }
     }
@@ -523,8 +544,14 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
       double v = pv;
       if (i == lane) v += lds_f64(sb + 8u * (DL::dg + lane));
       const uint32_t ji = sb + 8u * (DL::Js + i), jl = sb + 8u * (DL::Js + lane), cf = sb + 8u * DL::cf;
-      for (int r = 0; r < MP; r++)
-        v = fma(lds_f64(cf + 8u * r) * lds_f64(jl + 8u * (r * LDJ)), lds_f64(ji + 8u * (r * LDJ)), v);
+      double v2 = 0.0;
+#pragma unroll 4
+      for (int r = 0; r < MP; r += 2) {
+        const double2 cr = lds_v2(cf + 8u * r);
+        v = fma(cr.x * lds_f64(jl + 8u * (r * LDJ)), lds_f64(ji + 8u * (r * LDJ)), v);
+        if (r + 1 < MP) v2 = fma(cr.y * lds_f64(jl + 8u * ((r + 1) * LDJ)), lds_f64(ji + 8u * ((r + 1) * LDJ)), v2);
+      }
+      v += v2;
       sts_f64(sb + 8u * (DL::Ph + i * NP + lane), pv);
       sts_f64(sb + 8u * (DL::Si + i * NP + lane), v);  // in place: every element reads only itself from Si
     }
