@@ -221,6 +221,11 @@ def run_b200_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything libraries print meanwhile (NCCL's version banner)
+    # goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference "
                          "for the CPU arm)")
@@ -411,7 +416,10 @@ def run_b200_arm(args):
                    "team": eng.team, "smem_bytes": eng.smem_bytes, "ctas_per_sm": eng.occupancy,
                    "gen_seconds": t_gen},
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
