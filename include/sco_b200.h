@@ -43,6 +43,9 @@ extern "C" {
 #define SCO_FAM_QUADFORM 1 /* f_j = 0.5 x'P_j x + a_j'x ; par = P packed-upper [m][n(n+1)/2], a [m][n] */
 #define SCO_FAM_CIRCLE2D 2 /* f_{t,k} = R_k - |p_t - c_k| ; ipar = {T, K} ; par = c [K][2], R [K]      */
 #define SCO_FAM_FK7 3      /* flange position of a 7-link DH chain on x[n-7:n], finite-difference Jacobian */
+#define SCO_FAM_VM 4       /* rows given as stack programs (sco_py_b200/sym.py): par = m row offsets, then
+                              (opcode, operand) pairs; ipar = {n, m, instructions}; finite-difference Jacobian,
+                              like a black-box Expr without grad (expr.py:61-69) */
 
 #define SCO_CNT_LEQ 0 /* LEqExpr -> hinge penalty, one slack per row  (expr.py:353-371) */
 #define SCO_CNT_EQ 1  /* EqExpr  -> abs penalty, two slacks per row   (expr.py:314-332) */
@@ -105,6 +108,11 @@ typedef struct {
   const double *shared;         /* host, shared_len doubles */
   const int32_t *group_overlap; /* host, n_groups*n_groups or NULL */
   sco_block_desc blocks[SCO_MAX_BLOCKS];
+  /* non-quadratic objective term (prob.py:97-103 _nonquad_obj_exprs): one scalar stack program, convexified to
+   * degree 2 every SQP iteration -- finite-difference gradient and Hessian, eigenvalue shift (expr.py:102-156) */
+  sco_field obj_prog;
+  int32_t obj_prog_len; /* instructions; 0 = none */
+  int32_t pad_;
 } sco_structure_desc;
 
 typedef struct {

@@ -96,3 +96,40 @@ def fk7_pos(qj):
 def fk7_f(x):
     """Rows 0..2: flange position for the joints of the LAST time-step (x[-7:])."""
     return fk7_pos(x[-7:, 0]).reshape(3, 1)
+
+
+# ---------------------------------------------------------------- VM (stack programs, C1 toy problems)
+# Independent restatement of the interpreter of sco_py_b200/sym.py (the product's host code): program =
+# m row offsets, then (opcode, operand) pairs; opcodes END 0, PUSH_X 1, PUSH_C 2, ADD 3, SUB 4, MUL 5,
+# DIV 6, NEG 7, POWI 8, SQRT 9, LOG 10, EXP 11, SIN 12, COS 13.
+
+
+def vm_f(x, prog, m):
+    import math
+    xv = np.asarray(x, dtype=float).ravel()
+    ins = np.asarray(prog[m:], dtype=float).reshape(-1, 2)
+    out = np.zeros((m, 1))
+    unary = {9: math.sqrt, 10: math.log, 11: math.exp, 12: math.sin, 13: math.cos}
+    for r in range(m):
+        pc, stack = int(prog[r]), []
+        while int(ins[pc, 0]) != 0:
+            op, arg = int(ins[pc, 0]), float(ins[pc, 1])
+            pc += 1
+            if op == 1:
+                stack.append(float(xv[int(arg)]))
+            elif op == 2:
+                stack.append(arg)
+            elif op in (3, 4, 5, 6):
+                b, a = stack.pop(), stack.pop()
+                stack.append(a + b if op == 3 else a - b if op == 4 else a * b if op == 5 else a / b)
+            elif op == 7:
+                stack.append(-stack.pop())
+            elif op == 8:
+                a, v = stack.pop(), 1.0
+                for _ in range(int(arg)):
+                    v *= a
+                stack.append(v)
+            else:
+                stack.append(unary[op](stack.pop()))
+        out[r, 0] = stack.pop()
+    return out

@@ -46,6 +46,9 @@ def build_prob(ref, st, row, x0):
     var = ref["variable"].Variable(ovars, value=np.asarray(x0, dtype=float).reshape(n, 1))
     prob.add_var(var)
     prob.add_obj_expr(ex.BoundExpr(ex.QuadExpr(pp.Q, pp.q.reshape(1, n), np.array([[pp.c]])), var))
+    if pp.obj_prog is not None:  # black-box objective term, as tests/sco_osqp/test_solver.py:66-68 adds it
+        import families as fam
+        prob.add_obj_expr(ex.BoundExpr(ex.Expr(lambda x: fam.vm_f(x, pp.obj_prog, 1)), var))
     if st.m_lin:
         A = pp.A_lin.toarray()
         eq = np.isclose(pp.l_lin, pp.u_lin) & np.isfinite(pp.l_lin)
@@ -66,7 +69,7 @@ def build_prob(ref, st, row, x0):
             r = e
     for b in pp.blocks:
         blk = b.blk
-        grad = None if blk.family == port.FAM_FK7 else b.grad
+        grad = None if blk.family in (port.FAM_FK7, port.FAM_VM) else b.grad
         e = ex.Expr(b.f, grad)
         cnt = (ex.EqExpr if blk.cnt_type == port.CNT_EQ else ex.LEqExpr)(e, b.val)
         gids = None

@@ -38,7 +38,7 @@ import families as fam  # noqa: E402  (oracle/families.py)
 import numdifftools as nd  # noqa: E402  (oracle/shims/numdifftools)
 import osqp as osqp_shim  # noqa: E402  (oracle/shims/osqp)
 
-FAM_QUADFORM, FAM_CIRCLE2D, FAM_FK7 = 1, 2, 3
+FAM_QUADFORM, FAM_CIRCLE2D, FAM_FK7, FAM_VM = 1, 2, 3, 4
 CNT_LEQ, CNT_EQ = 0, 1
 
 DEFAULT_SOLVER = dict(  # sco_py/sco_osqp/solver.py:17-28
@@ -84,6 +84,12 @@ class _BlockFn(object):
             self.f = fam.fk7_f
             # no analytic gradient: expr.py:86-87 -> numdifftools.Jacobian
             self.grad = lambda x: nd.Jacobian(lambda v: fam.fk7_f(v.reshape(n, 1)).ravel())(x)
+        elif blk.family == FAM_VM:
+            m, n_instr = blk.m, blk.ipar[2]
+            prog = _field(st, blk.par, row, m + 2 * n_instr)
+            self.f = lambda x: fam.vm_f(x, prog, m)
+            # a black box without analytic gradient: expr.py:86-87 -> numdifftools.Jacobian
+            self.grad = lambda x: nd.Jacobian(lambda v: fam.vm_f(v, prog, m).ravel())(x)
         else:
             raise NotImplementedError(blk.family)
 
@@ -111,6 +117,13 @@ class PortProblem(object):
             self.A_lin = sp.csr_matrix((0, n))
             self.l_lin = self.u_lin = np.zeros(0)
         self.blocks = [_BlockFn(st, b, row) for b in st.blocks]
+        # non-quadratic objective term (prob.py:97-103 -> _nonquad_obj_exprs), a stack program
+        self.obj_prog = None
+        if getattr(st, "obj_prog_len", 0):
+            self.obj_prog = _field(st, st.obj_prog, row, 1 + 2 * st.obj_prog_len)
+        self.Hq = None  # its convex quadratic model (expr.py:143-153): 0.5 x'Hq x + aq x + bq
+        self.aq = None
+        self.bq = 0.0
         self.x = np.asarray(x0, dtype=float).reshape(n, 1).copy()
         self.x_saved = None
         # penalty-QP bookkeeping
@@ -124,8 +137,18 @@ class PortProblem(object):
 
     # -- objective / merit ------------------------------------------------
     def objective(self, x):
-        # QuadExpr.eval, expr.py:205-206
-        return float(0.5 * x[:, 0] @ (self.Q @ x[:, 0]) + self.q @ x[:, 0] + self.c)
+        # QuadExpr.eval, expr.py:205-206 (+ Expr.eval of the non-quadratic term, prob.py:573-574)
+        v = float(0.5 * x[:, 0] @ (self.Q @ x[:, 0]) + self.q @ x[:, 0] + self.c)
+        if self.obj_prog is not None:
+            v += float(fam.vm_f(x, self.obj_prog, 1)[0, 0])
+        return v
+
+    def objective_model(self, x):
+        # quadratic terms + the degree-2 model of the non-quadratic one (prob.py:624-626)
+        v = float(0.5 * x[:, 0] @ (self.Q @ x[:, 0]) + self.q @ x[:, 0] + self.c)
+        if self.obj_prog is not None:
+            v += float(0.5 * x[:, 0] @ (self.Hq @ x[:, 0]) + self.aq @ x[:, 0] + self.bq)
+        return v
 
     def group_vec(self, per_block_sums):
         g = np.zeros(self.st.n_groups)
@@ -152,7 +175,7 @@ class PortProblem(object):
             sums.append(float(np.sum(pen)))
         if vectorize:
             return self.group_vec(sums)
-        value = self.objective(self.x)
+        value = self.objective_model(self.x)
         for s in sums:
             value += mu * s
         return value
@@ -165,6 +188,16 @@ class PortProblem(object):
 
     # -- convexification + penalty bookkeeping ------------------------------
     def convexify(self):  # prob.py:522-544 ; expr.py:139-142, 327-328, 366-367
+        if self.obj_prog is not None:  # Expr.convexify degree 2, expr.py:143-153
+            flat = lambda v: fam.vm_f(v, self.obj_prog, 1).ravel()
+            H = nd.Hessian(flat)(self.x[:, 0].copy())
+            lam = float(np.min(np.linalg.eigvalsh(H)))
+            if lam < 0:
+                H = H - np.eye(self.n) * lam
+            g = nd.Jacobian(flat)(self.x)  # (1, n)
+            self.Hq = H
+            self.aq = (g - self.x.T @ H)[0]
+            self.bq = float(0.5 * self.x[:, 0] @ (H @ self.x[:, 0]) - g[0] @ self.x[:, 0] + flat(self.x)[0])
         self.J, self.b = [], []
         for b in self.blocks:
             J = np.asarray(b.grad(self.x), dtype=float)
@@ -192,6 +225,9 @@ class PortProblem(object):
         else:
             P[:n, :n] = 0.5 * (self.Q + self.Q.T)
             qv[:n] = self.q
+            if self.obj_prog is not None and self.Hq is not None:  # prob.py:348-367
+                P[:n, :n] += 0.5 * (self.Hq + self.Hq.T)
+                qv[:n] += self.aq
         rows = []
         lo = []
         hi = []

@@ -29,7 +29,8 @@ class CStructure(ctypes.Structure):
                 ("stride", c_i64), ("shared_len", c_i64),
                 ("Q", CField), ("q", CField), ("c", CField), ("lin_l", CField), ("lin_u", CField),
                 ("lin_rowptr", c_vp), ("lin_col", c_vp), ("lin_val", c_vp), ("shared", c_vp),
-                ("group_overlap", c_vp), ("blocks", CBlock * MAX_BLOCKS)]
+                ("group_overlap", c_vp), ("blocks", CBlock * MAX_BLOCKS),
+                ("obj_prog", CField), ("obj_prog_len", c_i32), ("pad_", c_i32)]
 
 
 class CSettings(ctypes.Structure):

@@ -28,6 +28,7 @@ class Compiled(object):
         self.c = 0.0
         self.lin_A = self.lin_l = self.lin_u = None
         self.blocks = []         # (family expr, cnt_type, val[m], group ids)
+        self.obj_prog = None     # SymExpr of a non-quadratic objective
         self.gids = []
 
 
@@ -74,9 +75,19 @@ def compile_problem(prob):
                 "AffExpr objectives: the OSQP backend of the reference turns them into penalty terms scaled by "
                 "the penalty coefficient (prob.py:220-221,240-249; SURVEY.md quirk C-4).  Fold the linear term "
                 "into QuadExpr.A instead.")
-    if prob._nonquad_obj_exprs:
-        raise UnsupportedProblem("non-quadratic objectives (finite-difference Hessian + eigenvalue shift, "
-                                 "expr.py:143-153) have no device kernel yet")
+    if prob._nonquad_obj_exprs:  # convexified to degree 2 on the device (expr.py:143-153)
+        if len(prob._nonquad_obj_exprs) > 1:
+            raise UnsupportedProblem("more than one non-quadratic objective term: add them up in one SymExpr")
+        b = prob._nonquad_obj_exprs[0]
+        cols = _columns(b.var, col_of)
+        if not (isinstance(b.expr, E.SymExpr) and b.expr.m == 1 and cols.size == n and
+                np.array_equal(cols, np.arange(n))):
+            raise UnsupportedProblem("a non-quadratic objective must be a scalar SymExpr (sco_py_b200.sym) bound to "
+                                     "a Variable that holds all scalar variables in QP order; black-box callables "
+                                     "cannot run on the device and there is no CPU fallback")
+        if n > 16:
+            raise UnsupportedProblem("non-quadratic objectives are limited to 16 variables (serial eigenvalue shift)")
+        cp.obj_prog = b.expr
     # ---- linear constraints
     rows_A, rows_l, rows_u = [], [], []
     for b, kind in prob._lin_cnt_exprs:
@@ -138,7 +149,9 @@ def compile_batch(probs):
                 (c.lin_A is None) == (c0.lin_A is None) and
                 (c.lin_A is None or (c.lin_A.shape == c0.lin_A.shape and np.array_equal(c.lin_A, c0.lin_A))) and
                 all(a[0].family == b[0].family and a[0].m == b[0].m and a[1] == b[1] and a[3] == b[3] and
-                    list(a[0].ipar) == list(b[0].ipar) for a, b in zip(c.blocks, c0.blocks)))
+                    list(a[0].ipar) == list(b[0].ipar) for a, b in zip(c.blocks, c0.blocks)) and
+                (c.obj_prog is None) == (c0.obj_prog is None) and
+                (c.obj_prog is None or c.obj_prog.n_instr == c0.obj_prog.n_instr))
         if not same:
             raise UnsupportedProblem("problem %d of the batch does not share the structure of problem 0" % i)
     shared_parts, shared_off = [], 0
@@ -179,6 +192,14 @@ def compile_batch(probs):
         fills.append((lf, lambda c: c.lin_l))
         fills.append((uf, lambda c: c.lin_u))
         kw = dict(m_lin=m_lin, lin_rowptr=rp, lin_col=ci, lin_val=cv, lin_l=lf, lin_u=uf)
+    if c0.obj_prog is not None:
+        p0 = c0.obj_prog.params()
+        if B > 1 and all(np.array_equal(c.obj_prog.params(), p0) for c in cps[1:]):
+            of = shared_field(p0)
+        else:
+            of = own_field(p0.size)
+            fills.append((of, lambda c: c.obj_prog.params()))
+        kw.update(obj_prog=of, obj_prog_len=c0.obj_prog.n_instr)
     blocks = []
     for bi, (fam, ctype, val, gids) in enumerate(c0.blocks):
         p0 = fam.params()
@@ -220,7 +241,7 @@ def signature(st):
     lin = None
     if st.m_lin:
         lin = (st.lin_rowptr.tobytes(), st.lin_col.tobytes(), st.lin_val.tobytes(), fld(st.lin_l), fld(st.lin_u))
-    return (st.n, st.stride, fld(st.Q), fld(st.q), fld(st.c), st.m_lin, lin, st.n_groups,
+    return (st.n, st.stride, fld(st.Q), fld(st.q), fld(st.c), fld(st.obj_prog), st.obj_prog_len, st.m_lin, lin, st.n_groups,
             None if st.group_overlap is None else st.group_overlap.tobytes(),
             None if st.shared is None else st.shared.tobytes(),
             tuple((b.family, b.cnt_type, b.m, fld(b.par), fld(b.val), tuple(b.ipar), b.group_mask, b.jw)

@@ -106,6 +106,7 @@ static void build_layout(DevStruct &S, int team) {
   L.red = take(8 * 16);
   L.msk = take((mp + 1) / 2);
   L.stage = take(std::max((team / 32) * S.stage_per_warp, 100));
+  L.Hq = take(S.obj_len ? n * n + 2 : 0); L.gq = take(S.obj_len ? n : 0);
   L.total = off;
 }
 
@@ -200,6 +201,8 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   S.stride = desc->stride;
   S.Q = cvt(desc->Q); S.q = cvt(desc->q); S.c = cvt(desc->c);
   S.lin_l = cvt(desc->lin_l); S.lin_u = cvt(desc->lin_u);
+  S.objp = cvt(desc->obj_prog); S.obj_len = desc->obj_prog_len > 0 && desc->obj_prog.off >= 0 ? desc->obj_prog_len : 0;
+  if (S.obj_len && n > 16) { delete h; return fail(SCO_ERR_UNSUPPORTED, "non-quadratic objectives are limited to 16 variables"); }
   for (int g = 0; g < desc->n_groups; g++) {
     int bits = 0;
     if (desc->group_overlap)
@@ -225,6 +228,9 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
     } else if (b.family == SCO_FAM_FK7) {
       jw = 7;
       if (b.m != 3 || n < 7) { delete h; return fail(SCO_ERR_ARG, "FK7: m must be 3 and n >= 7"); }
+    } else if (b.family == SCO_FAM_VM) {
+      jw = n;
+      if (b.ipar[0] != n || b.ipar[1] != b.m || b.ipar[2] <= 0) { delete h; return fail(SCO_ERR_ARG, "VM: ipar must be {n, m, instructions}"); }
     } else { delete h; return fail(SCO_ERR_UNSUPPORTED, "unknown constraint family %d", b.family); }
     if (jw > 32) { delete h; return fail(SCO_ERR_UNSUPPORTED, "Jacobian rows wider than 32 entries are not supported (n=%d)", n); }
     d.jw = jw;
@@ -237,7 +243,7 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
       row_gmask.push_back(b.group_mask);
       for (int k = 0; k < jw; k++) {
         int col = 0;
-        if (b.family == SCO_FAM_QUADFORM) col = k;
+        if (b.family == SCO_FAM_QUADFORM || b.family == SCO_FAM_VM) col = k;
         else if (b.family == SCO_FAM_CIRCLE2D) col = 2 * (r / b.ipar[1]) + k;
         else col = n - 7 + k;
         jcol.push_back(col);
@@ -297,7 +303,7 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   if (rc) { sco_destroy(h); return SCO_ERR_CUDA; }
   // ---- dense fast path: one dense hinge block, no linear rows, sizes within the instantiated table
   S.dense_kind = 0;
-  if (desc->m_lin == 0 && desc->n_blocks == 1 && desc->blocks[0].family == SCO_FAM_QUADFORM &&
+  if (desc->m_lin == 0 && S.obj_len == 0 && desc->n_blocks == 1 && desc->blocks[0].family == SCO_FAM_QUADFORM &&
       desc->blocks[0].cnt_type == SCO_CNT_LEQ) {
     static const int table[][2] = {{8, 6}, {12, 16}, {20, 30}, {32, 32}};  // keep in sync with sco_qp_dense.cuh
     for (int k = 0; k < 4; k++)

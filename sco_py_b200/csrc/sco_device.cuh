@@ -51,6 +51,7 @@ struct Layout {
   int red;    // reduction scratch: 8 warps * 8 values
   int msk;    // m_nl uint32 (counted in doubles, rounded up)
   int stage;  // per-warp staging buffers for family evaluation
+  int Hq, gq;  // degree-2 model of a non-quadratic objective: H+ (n*n, then b at [n*n]), linear term (n)
   int total;  // doubles
 };
 
@@ -94,6 +95,8 @@ struct DevStruct {
   int stage_per_warp;  // doubles
   long long stride;
   DevField Q, q, c, lin_l, lin_u;
+  DevField objp;       // non-quadratic objective: stack program (1 row)
+  int obj_len, pad2_;  // its instruction count, 0 = none
   // linear rows: CSR + CSC (entry index into lin_val / Als)
   const int *lin_rowptr, *lin_col, *lin_cptr, *lin_centry, *lin_crow;
   const double *lin_val;
@@ -229,6 +232,7 @@ struct QPW {
   Sh red;
   ShU32 msk;
   Sh stage;
+  Sh Hq, gq;
   Sh xc;  // current SQP iterate, n doubles appended after the layout
 
   __device__ __forceinline__ void bind(const Layout &L) {
@@ -246,6 +250,7 @@ struct QPW {
     red = Sh{L.red};
     msk = ShU32{L.msk};
     stage = Sh{L.stage};
+    Hq = Sh{L.Hq}; gq = Sh{L.gq};
     xc = Sh{L.total};
   }
 };

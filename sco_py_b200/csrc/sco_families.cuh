@@ -12,6 +12,7 @@
 #define FAM_QUADFORM 1
 #define FAM_CIRCLE2D 2
 #define FAM_FK7 3
+#define FAM_VM 4
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -124,6 +125,90 @@ __device__ void eval_fk7(const DevStruct &S, const DevBlock &B, const double *ta
   }
 }
 
+
+// ---- VM: rows given as stack programs (sco_py_b200/sym.py).  Program = m row offsets, then
+// (opcode, operand) pairs of doubles; opcodes END 0, PUSH_X 1, PUSH_C 2, ADD 3, SUB 4, MUL 5, DIV 6,
+// NEG 7, POWI 8, SQRT 9, LOG 10, EXP 11, SIN 12, COS 13.  Up to two variables may be replaced by
+// given values (the perturbed points of the finite differences) without copying x.
+#define SCO_VM_STACK 16
+#define SCO_FD_JAC_STEP 5.477420592293901e-07    // eps^(1/2.5): numdifftools base step, first derivatives
+#define SCO_FD_HESS_STEP 9.843133202303692e-03  // eps^(1/7.8): second derivatives (oracle/shims/numdifftools)
+
+static __device__ __noinline__ double vm_eval(const double *prog, int m, int row, Sh x, int pi, double vi, int pj, double vj) {
+  const double *ins = prog + m;
+  int pc = (int)prog[row];
+  double stk[SCO_VM_STACK];
+  int sp = 0;
+  for (;;) {
+    const int op = (int)ins[2 * pc];
+    const double arg = ins[2 * pc + 1];
+    pc++;
+    if (op == 0) break;
+    if (op == 1) {
+      const int i = (int)arg;
+      stk[sp++] = i == pi ? vi : (i == pj ? vj : x[i]);
+    } else if (op == 2) {
+      stk[sp++] = arg;
+    } else if (op <= 6) {
+      const double b = stk[--sp], a = stk[sp - 1];
+      stk[sp - 1] = op == 3 ? a + b : op == 4 ? a - b : op == 5 ? a * b : a / b;
+    } else if (op == 7) {
+      stk[sp - 1] = -stk[sp - 1];
+    } else if (op == 8) {
+      const double a = stk[sp - 1];
+      double v = 1.0;
+      for (int k = (int)arg; k > 0; k--) v = v * a;
+      stk[sp - 1] = v;
+    } else {
+      const double a = stk[sp - 1];
+      stk[sp - 1] = op == 9 ? sqrt(a) : op == 10 ? log(a) : op == 11 ? exp(a) : op == 12 ? sin(a) : cos(a);
+    }
+  }
+  return stk[sp - 1];
+}
+
+// d f_row / d x_j by two central differences, Richardson-combined (numdifftools.Jacobian as called at
+// expr.py:67; the scheme of oracle/shims/numdifftools.jacobian_fd)
+static __device__ double vm_fd1(const double *prog, int m, int row, Sh x, int j) {
+  const double xj = x[j];
+  const double h0 = SCO_FD_JAC_STEP * fmax(log1p(fabs(xj)), 1.0);
+  double est[2];
+  for (int k = 0; k < 2; k++) {
+    const double h = h0 * (k ? 2.0 : 1.0);
+    const double xp = xj + h, xm = xj - h;
+    est[k] = (vm_eval(prog, m, row, x, j, xp, -1, 0.0) - vm_eval(prog, m, row, x, j, xm, -1, 0.0)) / (xp - xm);
+  }
+  return (4.0 * est[0] - est[1]) / 3.0;
+}
+
+// d2 f / d x_i d x_j of a scalar program: central second differences at h and 2h, Richardson-combined
+// (numdifftools.Hessian as called at expr.py:108; oracle/shims/numdifftools.hessian_fd)
+static __device__ double vm_fd2(const double *prog, Sh x, int i, int j, double f0) {
+  const double xi = x[i], xj = x[j];
+  const double hi0 = SCO_FD_HESS_STEP * fmax(log1p(fabs(xi)), 1.0), hj0 = SCO_FD_HESS_STEP * fmax(log1p(fabs(xj)), 1.0);
+  double est[2];
+  for (int k = 0; k < 2; k++) {
+    const double hi = hi0 * (k ? 2.0 : 1.0), hj = hj0 * (k ? 2.0 : 1.0);
+    if (i == j) {
+      est[k] = (vm_eval(prog, 1, 0, x, i, xi + 2.0 * hi, -1, 0.0) - 2.0 * f0 + vm_eval(prog, 1, 0, x, i, xi - 2.0 * hi, -1, 0.0)) /
+               (4.0 * hi * hi);
+    } else {
+      est[k] = (vm_eval(prog, 1, 0, x, i, xi + hi, j, xj + hj) - vm_eval(prog, 1, 0, x, i, xi + hi, j, xj - hj) -
+                vm_eval(prog, 1, 0, x, i, xi - hi, j, xj + hj) + vm_eval(prog, 1, 0, x, i, xi - hi, j, xj - hj)) /
+               (4.0 * hi * hj);
+    }
+  }
+  return (4.0 * est[0] - est[1]) / 3.0;
+}
+
+template <int TEAM>
+__device__ void eval_vm(const DevStruct &S, const DevBlock &B, const double *prog, Sh x, Sh f, double *Jout) {
+  const int n = S.n, m = B.m;
+  for (int r = threadIdx.x; r < m; r += TEAM) f[r] = vm_eval(prog, m, r, x, -1, 0.0, -1, 0.0);
+  if (Jout)
+    for (int e = threadIdx.x; e < m * n; e += TEAM) Jout[e] = vm_fd1(prog, m, e / n, x, e % n);
+}
+
 // Evaluate every block at x: fv[row] = f_row(x); if Jg != null also the stored Jacobian entries.
 // Ends with a team sync.
 template <int TEAM>
@@ -136,6 +221,7 @@ __device__ __noinline__ void eval_blocks(const DevStruct &S, const double *prm, 
     if (B.family == FAM_QUADFORM) eval_quadform<TEAM>(S, B, par, x, f, J, stage);
     else if (B.family == FAM_CIRCLE2D) eval_circle2d<TEAM>(S, B, par, x, f, J);
     else if (B.family == FAM_FK7) eval_fk7<TEAM>(S, B, par, x, f, J, stage);
+    else if (B.family == FAM_VM) eval_vm<TEAM>(S, B, par, x, f, J);
   }
   Team<TEAM>::sync();
 }

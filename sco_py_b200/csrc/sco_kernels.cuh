@@ -124,6 +124,7 @@ k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st
     a.kd = kdup ? (double)kdup[b] : 1.0;
     a.use_pen = use_pen;
     a.closest = closest;
+    a.has_hq = 0;
     QPSolver<TEAM, DK> qp(S, st, w, a);
     QPResult r = qp.solve();
     const int nq = use_pen ? S.n_q : n;

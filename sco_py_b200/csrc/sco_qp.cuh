@@ -29,6 +29,7 @@ struct QPArgs {
   double kd;          // copies of every penalty row
   int use_pen;        // 0: no penalty rows / slacks (closest feasible point)
   int closest;        // objective |x - xs|^2
+  int has_hq;         // add the degree-2 model of a non-quadratic objective term (w.Hq, w.gq)
 };
 
 struct QPResult {
@@ -87,8 +88,9 @@ struct QPSolver {
 
   __device__ __forceinline__ double psym(int i, int j) const {
     if (a.closest) return i == j ? 2.0 : 0.0;
-    if (!Qg) return 0.0;
-    return 0.5 * (Qg[i * n + j] + Qg[j * n + i]);
+    double v = Qg ? 0.5 * (Qg[i * n + j] + Qg[j * n + i]) : 0.0;
+    if (a.has_hq) v += 0.5 * (w.Hq[i * n + j] + w.Hq[j * n + i]);  // prob.py:348-367
+    return v;
   }
 
   // A' * (row-space vector) for user variable j: linear rows (vl) and penalty rows (vp; the caller
@@ -130,7 +132,7 @@ struct QPSolver {
     const double *llg = field_ptr(S, S.lin_l, a.prm), *ulg = field_ptr(S, S.lin_u, a.prm);
     for (int e = tid; e < n * n; e += TEAM) w.Sm[e] = psym(e / n, e % n);
     for (int j = tid; j < n; j += TEAM) {
-      w.qh[j] = a.closest ? -2.0 * w.xs[j] : (qg ? qg[j] : 0.0);
+      w.qh[j] = a.closest ? -2.0 * w.xs[j] : (qg ? qg[j] : 0.0) + (a.has_hq ? w.gq[j] : 0.0);
       w.D[j] = 1.0;
       w.bx[j] = 1.0;
       w.Eb[j] = 1.0;
@@ -377,8 +379,8 @@ struct QPSolver {
       u[0] = fmax(u[0], fabs(ax - z)); u[1] = fmax(u[1], fabs(z)); u[2] = fmax(u[2], fabs(ax));
       double px = 0.0;
       if (a.closest) px = 2.0 * w.xt[j];
-      else if (Qg)
-        for (int k = 0; k < n; k++) px += 0.5 * (Qg[k * n + j] + Qg[j * n + k]) * w.xt[k];
+      else if (Qg || a.has_hq)
+        for (int k = 0; k < n; k++) px += psym(k, j) * w.xt[k];
       px *= c * w.D[j];
       const double aty = gatherAT(j, w.yl, w.wp) + w.bx[j] * w.yb[j];
       const double di = 1.0 / w.D[j], q = w.qh[j];
@@ -485,8 +487,8 @@ struct QPSolver {
       for (int j = tid; j < n; j += TEAM) {
         double px = 0.0;
         if (a.closest) px = 2.0 * w.xt[j];
-        else if (Qg)
-          for (int k = 0; k < n; k++) px += 0.5 * (Qg[k * n + j] + Qg[j * n + k]) * w.xt[k];
+        else if (Qg || a.has_hq)
+          for (int k = 0; k < n; k++) px += psym(k, j) * w.xt[k];
         pv[0] = fmax(pv[0], fabs(c * px));  // Dinv .* (c D Psym D dx) = c * Psym (D dx)
       }
       Team<TEAM>::reduce_max(pv, w.red);

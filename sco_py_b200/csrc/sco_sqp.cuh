@@ -38,8 +38,8 @@ struct SqpSolver {
 
   __device__ __forceinline__ void sync() { Team<TEAM>::sync(); }
 
-  // QuadExpr.eval (expr.py:205-206): 0.5 x'Qx + q'x + c at xc
-  __device__ double objective() {
+  // quadratic part of the objective at xc: 0.5 x'Qx + q'x + c (QuadExpr.eval, expr.py:205-206)
+  __device__ double objective_quad() {
     const double *Qg = field_ptr(S, S.Q, prm), *qg = field_ptr(S, S.q, prm), *cg = field_ptr(S, S.c, prm);
     double v[1] = {0.0};
     for (int k = tid; k < n; k += TEAM) {
@@ -50,6 +50,92 @@ struct SqpSolver {
     }
     Team<TEAM>::reduce_sum(v, w.red);
     return v[0] + (cg ? cg[0] : 0.0);
+  }
+
+  // exact objective: quadratic terms + the non-quadratic term (prob.py:573-574)
+  __device__ double objective() {
+    double v = objective_quad();
+    if (S.obj_len) v += vm_eval(field_ptr(S, S.objp, prm), 1, 0, xc, -1, 0.0, -1, 0.0);
+    return v;
+  }
+
+  // objective of the convex model: quadratic terms + the degree-2 model of the non-quadratic term at
+  // the last convexification (prob.py:624-626)
+  __device__ double objective_model() {
+    double v = objective_quad();
+    if (S.obj_len) {
+      double t[1] = {0.0};
+      for (int k = tid; k < n; k += TEAM) {
+        double acc = 0.0;
+        for (int j = 0; j < n; j++) acc += w.Hq[j * n + k] * xc[j];
+        t[0] += xc[k] * (0.5 * acc + w.gq[k]);
+      }
+      Team<TEAM>::reduce_sum(t, w.red);
+      v += t[0] + w.Hq[n * n];
+    }
+    return v;
+  }
+
+  // Expr.convexify degree 2 of the non-quadratic objective term at xc (expr.py:143-153):
+  // H = numeric Hessian shifted by -min(lambda_min, 0) I, A = grad - x'H, b = 0.5 x'Hx - grad.x + f.
+  // Leaves H in w.Hq (n x n), b in w.Hq[n*n], A in w.gq.  Uses w.Sm as scratch.
+  __device__ void convexify_objective() {
+    const double *prog = field_ptr(S, S.objp, prm);
+    const double f0 = vm_eval(prog, 1, 0, xc, -1, 0.0, -1, 0.0);
+    for (int e = tid; e < n * n; e += TEAM) {
+      const int i = e / n, j = e % n;
+      if (i <= j) {
+        const double h = vm_fd2(prog, xc, i, j, f0);
+        w.Hq[i * n + j] = h; w.Hq[j * n + i] = h;
+        w.Sm[i * n + j] = h; w.Sm[j * n + i] = h;
+      }
+    }
+    for (int j = tid; j < n; j += TEAM) w.xt[j] = vm_fd1(prog, 1, 0, xc, j);  // gradient
+    sync();
+    if (tid == 0) {  // smallest eigenvalue: cyclic Jacobi on the scratch copy (n <= 16)
+      for (int sweep = 0; sweep < 50; sweep++) {
+        double off = 0.0, dg = 0.0;
+        for (int p = 0; p < n; p++)
+          for (int q = 0; q < n; q++) (p == q ? dg : off) += w.Sm[p * n + q] * w.Sm[p * n + q];
+        if (off <= 1e-30 * dg || off == 0.0) break;
+        for (int p = 0; p < n - 1; p++)
+          for (int q = p + 1; q < n; q++) {
+            const double apq = w.Sm[p * n + q];
+            if (apq == 0.0) continue;
+            const double theta = (w.Sm[q * n + q] - w.Sm[p * n + p]) / (2.0 * apq);
+            const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+            for (int k = 0; k < n; k++) {  // columns p, q
+              const double akp = w.Sm[k * n + p], akq = w.Sm[k * n + q];
+              w.Sm[k * n + p] = c * akp - sn * akq;
+              w.Sm[k * n + q] = sn * akp + c * akq;
+            }
+            for (int k = 0; k < n; k++) {  // rows p, q
+              const double apk = w.Sm[p * n + k], aqk = w.Sm[q * n + k];
+              w.Sm[p * n + k] = c * apk - sn * aqk;
+              w.Sm[q * n + k] = sn * apk + c * aqk;
+            }
+          }
+      }
+      double lam = w.Sm[0];
+      for (int p = 1; p < n; p++) lam = fmin(lam, w.Sm[p * n + p]);
+      w.Hq[n * n + 1] = lam;
+    }
+    sync();
+    const double lam = w.Hq[n * n + 1];
+    if (lam < 0.0)
+      for (int j = tid; j < n; j += TEAM) w.Hq[j * n + j] -= lam;
+    sync();
+    double t[1] = {0.0};
+    for (int k = tid; k < n; k += TEAM) {
+      double acc = 0.0;
+      for (int j = 0; j < n; j++) acc += w.Hq[j * n + k] * xc[j];  // (x'H)_k
+      w.gq[k] = w.xt[k] - acc;
+      t[0] += xc[k] * (0.5 * acc - w.xt[k]);
+    }
+    Team<TEAM>::reduce_sum(t, w.red);
+    if (tid == 0) w.Hq[n * n] = t[0] + f0;
+    sync();
   }
 
   // violations from w.fv (raw f at xc): out[0] = sum, out[1] = max, out[2+g] = group sums
@@ -97,6 +183,7 @@ struct SqpSolver {
 
   // Prob.convexify at xc: fv, Jg, bb = f - J x - val ; first call freezes the sparsity masks
   __device__ void convexify(bool &mask_set) {
+    if (S.obj_len) convexify_objective();
     eval_blocks<TEAM>(S, prm, xc, w.fv, Jg, w.stage);
     for (int bi = 0; bi < S.n_blocks; bi++) {
       const DevBlock &B = S.blocks[bi];
@@ -136,7 +223,7 @@ struct SqpSolver {
       for (int j = tid; j < n; j += TEAM) { w.xs[j] = xc[j]; w.lb[j] = -INFINITY; w.ub[j] = INFINITY; }
       sync();
       QPArgs a;
-      a.prm = prm; a.Jg = nullptr; a.pi = 0.0; a.kd = 0.0; a.use_pen = 0; a.closest = 1;
+      a.prm = prm; a.Jg = nullptr; a.pi = 0.0; a.kd = 0.0; a.use_pen = 0; a.closest = 1; a.has_hq = 0;
       DevSettings d = st;
       d.eps_abs = 1e-6; d.eps_rel = 1e-9; d.max_iter = 100000; d.rho = 0.1; d.sigma = 5e-10;
       d.adaptive_rho = 0;
@@ -182,7 +269,7 @@ struct SqpSolver {
             for (int j = tid; j < n; j += TEAM) { w.lb[j] = w.xs[j] - delta; w.ub[j] = w.xs[j] + delta; }
             sync();
             QPArgs a;
-            a.prm = prm; a.Jg = Jg; a.pi = pi; a.kd = kd; a.use_pen = 1; a.closest = 0;
+            a.prm = prm; a.Jg = Jg; a.pi = pi; a.kd = kd; a.use_pen = 1; a.closest = 0; a.has_hq = S.obj_len != 0;
             QPSolver<TEAM, DK> qp(S, st, w, a);
             QPResult r = qp.solve();
             o.qp_solves++; o.admm_iters += r.iters; o.last_status = r.status;
@@ -195,7 +282,7 @@ struct SqpSolver {
             }
             model_sums(ms_);
             const double obj_new = objective();
-            const double model_merit = obj_new + mu * ms_[0];
+            const double model_merit = (S.obj_len ? objective_model() : obj_new) + mu * ms_[0];
             eval_blocks<TEAM>(S, prm, xc, w.fv, nullptr, w.stage);
             violation_sums(vs);
             const double new_merit = obj_new + mu * vs[0];

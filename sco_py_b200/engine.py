@@ -66,6 +66,7 @@ class Engine(object):
         cs.shared = hold(st.shared, np.float64) if st.shared is not None else None
         cs.Q, cs.q, cs.c = _field(st.Q), _field(st.q), _field(st.c)
         cs.lin_l, cs.lin_u = _field(st.lin_l), _field(st.lin_u)
+        cs.obj_prog, cs.obj_prog_len = _field(st.obj_prog), int(st.obj_prog_len)
         if st.m_lin:
             cs.lin_rowptr = hold(st.lin_rowptr, np.int32)
             cs.lin_col = hold(st.lin_col, np.int32)

@@ -10,6 +10,9 @@ change: say which family `f` belongs to,
     Expr(f, grad)                      ->  QuadFormExpr(P, a)          f_j = 0.5 x'P_j x + a_j'x
                                            CircleDistExpr(T, c, R)     f_tk = R_k - |p_t - c_k|
                                            FK7Expr(n)                  flange position of a 7-link chain
+                                           SymExpr(rows, n)            anything written with sco_py_b200.sym
+                                                                       (finite-difference derivatives, like a
+                                                                       black box without `grad`)
 
 Everything else (Variable, Prob.add_obj_expr / add_cnt_expr, BoundExpr, Solver.solve) is written as
 with the reference.  The family classes are still `Expr`s -- eval / grad / convexify work on the host
@@ -25,8 +28,8 @@ The rounded-x caches of the reference (expr.py:13,31-41: quirk C-6 of SURVEY.md)
 """
 import numpy as np
 
-from . import families_host
-from .structure import FAM_CIRCLE2D, FAM_FK7, FAM_QUADFORM
+from . import families_host, sym
+from .structure import FAM_CIRCLE2D, FAM_FK7, FAM_QUADFORM, FAM_VM
 
 DEFAULT_TOL = 1e-4
 
@@ -364,3 +367,27 @@ class FK7Expr(DeviceFamilyExpr):
 
     def params(self):
         return families_host.fk7_table()
+
+
+class SymExpr(DeviceFamilyExpr):
+    """Rows written in the expression language of sco_py_b200.sym, over ALL n variables.  No analytic
+    derivatives: Jacobians (constraints) and gradient + Hessian (a non-quadratic objective,
+    expr.py:102-156) are finite-differenced with the numdifftools scheme, on the device by the VM family
+    and on the host by `Expr.grad` / `Expr.hess` -- exactly what the reference does with `Expr(f)`."""
+
+    family = FAM_VM
+
+    def __init__(self, rows, n):
+        self.n = int(n)
+        self.rows = list(rows)
+        self.m = len(self.rows)
+        self.program, self.n_instr = sym.compile_rows(self.rows)
+        self.jw = self.n
+        self.ipar = [self.n, self.m, self.n_instr, 0, 0, 0, 0, 0]
+        Expr.__init__(self, self._f, None)
+
+    def _f(self, x):
+        return sym.eval_program(self.program, self.m, np.asarray(x).ravel()).reshape(self.m, 1)
+
+    def params(self):
+        return self.program

@@ -19,7 +19,7 @@ import numpy as np
 FAM_QUADFORM = 1   # f_j = 0.5 x'P_j x + a_j'x        (packed-upper P_j, then a_j)
 FAM_CIRCLE2D = 2   # f_{t,k} = R_k - ||p_t - c_k||    (centres K x 2, radii K)
 FAM_FK7 = 3        # flange position of a 7-link DH chain on x[-7:], FD Jacobian
-FAM_VM = 4         # byte-code expression (reserved)
+FAM_VM = 4         # stack program of sco_py_b200.sym, finite-difference Jacobian (dense rows)
 
 CNT_LEQ = 0        # LEqExpr  -> hinge penalty, 1 slack per row   (expr.py:353-371)
 CNT_EQ = 1         # EqExpr   -> abs penalty,   2 slacks per row  (expr.py:314-332)
@@ -63,6 +63,8 @@ class Structure:
     n_groups: int = 1
     group_overlap: Optional[np.ndarray] = None    # n_groups x n_groups 0/1 (prob.py:139-142)
     shared: Optional[np.ndarray] = None           # shared block
+    obj_prog: Field = field(default_factory=Field)  # non-quadratic objective: stack program (sym.py), 1 row
+    obj_prog_len: int = 0                           # its instruction count (0 = none)
 
     @property
     def m_nl(self):
@@ -84,6 +86,8 @@ class Structure:
             return np.stack([2 * t, 2 * t + 1], axis=1).astype(np.int32)
         if b.family == FAM_FK7:
             return np.tile(np.arange(n - 7, n, dtype=np.int32), (3, 1))
+        if b.family == FAM_VM:
+            return np.tile(np.arange(n, dtype=np.int32), (b.m, 1))
         raise NotImplementedError(b.family)
 
     def get(self, f: Field, params_row, size):

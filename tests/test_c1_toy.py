@@ -1,12 +1,14 @@
 """BASELINE.json configs[0]: the toy non-convex problems of the reference's own solver test
 (tests/sco_osqp/test_solver.py:91-169, hyper-parameters :15-25, pass mark atol 5e-4 on the optimum :87).
 
-Five of the nine have objective and constraints that are quadratic forms (prob0, 2, 3, 5, 6); they are
-written here with the device families (QuadExpr objective, QuadFormExpr constraints -- a linear g is a
-quadratic form with P = 0) exactly as helper_test_prob (:32-87) assembles them: one quadratic
-objective, one linear LEq row block, one nonlinear LEq block g, one nonlinear Eq block h, where absent
-pieces are the reference's placeholders (g = -1e5, h = 0).  The other four need a black-box objective
-(quartic, Rosenbrock, log): finite-difference Hessians are not on the device yet.
+All nine are assembled exactly as helper_test_prob (:32-87) does: one quadratic objective, one
+black-box objective term f, one linear LEq row block, one nonlinear LEq block g, one nonlinear Eq
+block h, absent pieces being the reference's placeholders (f = 0, g = -1e5, h = 0).
+  * "quadform" variants (prob0, 2, 3, 5, 6): f folded into the QuadExpr, g / h as QuadFormExpr
+    (a linear g is a quadratic form with P = 0) -- the closed-family path.
+  * "sym" variants (all nine): f, g, h written in the expression language of sco_py_b200.sym, i.e. black
+    boxes without analytic derivatives like the reference's lambdas: finite-difference Jacobians, and
+    for f the finite-difference Hessian + eigenvalue shift of Expr.convexify degree 2 (expr.py:143-153).
 """
 import numpy as np
 import pytest
@@ -14,7 +16,9 @@ import pytest
 import sqp_port
 from sco_py_b200 import batch
 from sco_py_b200 import workloads as W
-from sco_py_b200.expr import AffExpr, BoundExpr, EqExpr, LEqExpr, QuadExpr, QuadFormExpr
+import ref_builder
+from sco_py_b200 import sym
+from sco_py_b200.expr import AffExpr, BoundExpr, EqExpr, LEqExpr, QuadExpr, QuadFormExpr, SymExpr
 from sco_py_b200.sco_b200.osqp_utils import OSQPVar
 from sco_py_b200.sco_b200.prob import Prob
 from sco_py_b200.sco_b200.solver import Solver
@@ -102,3 +106,101 @@ def test_jittered_batch_of_toy_problems():
         _solver().solve_batch([b[0] for b in built], method="penalty_sqp")
         for prob, var, x_true in built:
             assert np.allclose(var.get_value()[:, 0], x_true, atol=5e-4), (name, var.get_value()[:, 0])
+
+
+# ------------------------------------------------------------------ all nine, as black boxes (sym)
+X = sym.variables(2)
+x1, x2 = X
+HEXROWS = [0.01 * (float(HEX_A[k, 0]) * x1 + float(HEX_A[k, 1]) * x2 - 1.0) for k in range(6)]
+SYM_PROBLEMS = {
+    # name: (x0, x_true, Q, q, A_ineq, b_ineq, f, g rows, h rows)       tests/sco_osqp/test_solver.py:91-169
+    "prob0": ([1.0, 1.0], [1.5, 1.5], Z, np.zeros((1, 2)), None, None, x1 ** 2 + x2 ** 2, [3 - x1 - x2], None),
+    "prob1": ([-2.0, 1.0], [1.0, 1.0], Z, np.zeros((1, 2)), None, None, (x2 - x1 ** 2) ** 2 + (1 - x1) ** 2,
+              [-1.5 - x2], None),
+    "prob2": ([10.0, 1.0], [0.0, 0.0], Z, np.zeros((1, 2)), None, None, x2 + 1e-5 + (x2 - x1) ** 2, [-x2], None),
+    "prob3": ([10.0, 1.0], [1.0, 1.0], Z, np.zeros((1, 2)), None, None, (1 - x1) ** 2, None, [10 * (x2 - x1 ** 2)]),
+    "prob4": ([2.0, 2.0], [0.0, np.sqrt(3)], Z, np.zeros((1, 2)), None, None, sym.log(1 + x1 ** 2) - x2, None,
+              [(1 + x1 ** 2) ** 2 + x2 ** 2 - 4]),
+    "prob5": ([0.0, 0.0], [1.0, np.tan(np.pi / 6)], Z, HEX_q, HEX_A, np.ones((6, 1)), None, None, None),
+    "prob6": ([0.0, 0.0], [1.0, np.tan(np.pi / 6)], 0.1 * np.eye(2), HEX_q, None, None, None, HEXROWS, None),
+    "prob7": ([0.0, 0.0], [2.0, 1.0], Z, np.zeros((1, 2)), None, None, x1 ** 4 + x2 ** 4, [3 - x1 - x2], [x1 - 2 * x2]),
+    "prob8": ([5.0, 5.0], [0.0, 0.0], np.eye(2), np.zeros((1, 2)), None, None, None,
+              [x1 ** 2 + x2 ** 2 - 4, -((x1 - 1) ** 2 + (x2 - 1) ** 2 - 0.25), -((x1 + 1) ** 2 + (x2 - 1) ** 2 - 0.25),
+               -(x1 ** 2 + 7 * (x2 + 1 - x1 ** 2 / 2) ** 2 - 0.8)], None),
+}
+
+
+def build_sym(name, x0=None):
+    x0_, x_true, Q, q, A_ineq, b_ineq, f, g, h = SYM_PROBLEMS[name]
+    x0 = np.array(x0_ if x0 is None else x0, dtype=float).reshape(2, 1)
+    prob = Prob()
+    ov = np.array([[OSQPVar("x1")], [OSQPVar("x2")]], dtype=object)
+    for v in ov[:, 0]:
+        prob.add_osqp_var(v)
+    var = Variable(ov, value=x0)
+    prob.add_var(var)
+    prob.add_obj_expr(BoundExpr(QuadExpr(Q, q, np.zeros((1, 1))), var))
+    prob.add_obj_expr(BoundExpr(SymExpr([f if f is not None else sym.Sym.wrap(0.0)], 2), var))    # zerofunc
+    if A_ineq is None:
+        A_ineq, b_ineq = np.zeros((1, N)), np.zeros((1, 1))
+    prob.add_cnt_expr(BoundExpr(LEqExpr(AffExpr(A_ineq, -b_ineq), np.zeros(b_ineq.shape)), var))
+    g = g if g is not None else [sym.Sym.wrap(-1e5)]                                               # neginffunc
+    prob.add_cnt_expr(BoundExpr(LEqExpr(SymExpr(g, 2), np.zeros((len(g), 1))), var))
+    h = h if h is not None else [sym.Sym.wrap(0.0)]                                                # zerofunc
+    prob.add_cnt_expr(BoundExpr(EqExpr(SymExpr(h, 2), np.zeros((len(h), 1))), var))
+    return prob, var, np.array(x_true)
+
+
+@pytest.mark.parametrize("name", sorted(SYM_PROBLEMS))
+def test_oracle_reaches_the_reference_answers_sym(name):
+    prob, var, x_true = build_sym(name)
+    st, params, x0, _ = batch.compile_batch([prob])
+    r = sqp_port.solve(st, params[0], x0[0], solver=W.SOLVER_SETTINGS)
+    assert np.allclose(r["x"], x_true, atol=5e-4), (name, r["x"])
+
+
+@pytest.mark.skipif(not ref_builder.reference_available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("name", ["prob1", "prob4", "prob7", "prob8"])
+def test_port_equals_the_unmodified_reference_on_black_box_objectives(name):
+    """The unmodified reference (Solver.solve on the shims) on the same functions as Python callables."""
+    prob, var, x_true = build_sym(name)
+    st, params, x0, _ = batch.compile_batch([prob])
+    a = sqp_port.solve(st, params[0], x0[0], solver=W.SOLVER_SETTINGS)
+    b = ref_builder.solve_with_reference(ref_builder.import_reference(), st, params[0], x0[0], solver=W.SOLVER_SETTINGS)
+    assert a["success"] == b["success"]
+    assert np.abs(a["x"] - b["x"]).max() <= 1e-7, (a["x"], b["x"])
+    assert np.allclose(b["x"], x_true, atol=5e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SYM_PROBLEMS))
+def test_device_reaches_the_reference_answers_sym(name):
+    prob, var, x_true = build_sym(name)
+    st, params, x0, _ = batch.compile_batch([prob])
+    ref = sqp_port.solve(st, params[0], x0[0], solver=W.SOLVER_SETTINGS)
+    ok = _solver().solve(prob, method="penalty_sqp")
+    assert ok == ref["success"], name
+    assert np.allclose(var.get_value()[:, 0], x_true, atol=5e-4), (name, var.get_value()[:, 0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["prob4", "prob8"])
+def test_vm_family_values_and_fd_jacobians_match_the_oracle(name):
+    """Stage level: the stack-program family on the device (values, finite-difference Jacobian, affine
+    offsets) against the oracle's interpreter + numdifftools shim."""
+    from sco_py_b200.engine import Engine
+    prob, var, _ = build_sym(name)
+    st, params, x0, _ = batch.compile_batch([prob])
+    eng = Engine(st)
+    f, J, b, obj = [t.cpu().numpy()[0] for t in eng.convexify(params, x0)]
+    pp = sqp_port.PortProblem(st, params[0], x0[0])
+    pp.convexify()
+    r0 = e0 = 0
+    for bi, blk in enumerate(st.blocks):
+        np.testing.assert_allclose(f[r0:r0 + blk.m], pp.blocks[bi].f(pp.x)[:, 0], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(J[e0:e0 + blk.m * blk.jw].reshape(blk.m, blk.jw), pp.J[bi], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(b[r0:r0 + blk.m], pp.b[bi][:, 0], rtol=1e-9, atol=1e-8)
+        r0 += blk.m
+        e0 += blk.m * blk.jw
+    assert abs(obj - pp.objective(pp.x)) <= 1e-12 * max(1.0, abs(obj))
+    eng.close()
