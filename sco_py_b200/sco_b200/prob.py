@@ -109,6 +109,9 @@ class Prob(object):
     def convexify(self):
         """Affine models of the nonlinear constraints at the current value (prob.py:522-544)."""
         s = self._dev()
+        if s["st"].obj_prog_len:
+            raise NotImplementedError("the step-by-step methods do not carry the degree-2 model of a non-quadratic "
+                                      "objective between calls; use Solver.solve (one kernel does the whole SQP)")
         if s["st"].m_nl == 0:
             return
         f, J, b, _ = s["eng"].convexify(s["params"], self._x())
