@@ -379,8 +379,9 @@ extern "C" int sco_solve_batch(sco_handle *h, int64_t B, const double *d_params,
                                const sco_settings *s, double *d_x_out, int32_t *d_verdict,
                                double *d_merit, double *d_objective, double *d_max_vio,
                                int32_t *d_stats, void *stream) {
-  if (!h || !s || !d_params || !d_x0 || !d_x_out || !d_verdict) return fail(SCO_ERR_ARG, "null argument");
-  if (B <= 0) return SCO_OK;
+  if (!h || !s) return fail(SCO_ERR_ARG, "null argument");
+  if (B <= 0) return SCO_OK;  // an empty batch is valid and touches nothing
+  if (!d_params || !d_x0 || !d_x_out || !d_verdict) return fail(SCO_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   DevSettings d = to_dev(s);
@@ -408,8 +409,9 @@ extern "C" int sco_solve_batch_host_async(sco_handle *h, int64_t B, const double
                                           const sco_settings *s, double *x_out, int32_t *verdict,
                                           double *merit, double *objective, double *max_vio,
                                           int32_t *stats, void *stream) {
-  if (!h || !s || !params || !x0 || !x_out || !verdict) return fail(SCO_ERR_ARG, "null argument");
+  if (!h || !s) return fail(SCO_ERR_ARG, "null argument");
   if (B <= 0) return SCO_OK;
+  if (!params || !x0 || !x_out || !verdict) return fail(SCO_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
   const int n = h->S.n;
   cudaStream_t st = (cudaStream_t)stream;

@@ -202,3 +202,44 @@ def test_prob_stage_methods_penalty_iteration():
         assert abs(prob.get_approx_value(mu) - pp.get_approx_value(mu)) <= 1e-6 * max(1.0, abs(pp.get_approx_value(mu)))
         assert abs(prob.get_value(mu) - pp.get_value(mu)) <= 1e-6 * max(1.0, abs(pp.get_value(mu)))
         assert np.allclose(prob.get_value(mu, vectorize=True), pp.get_value(mu, vectorize=True), atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_edge_cases_empty_batch_qp_only_problem_and_size_limits():
+    from sco_py_b200.engine import Engine, make_settings
+    from sco_py_b200.structure import Field
+    # empty batch: valid, returns empty results (the reference has no batch notion; ragged ends of a
+    # sharded batch produce it)
+    st, params, x0 = W.gen_qcqp(2, n=8, m=6)
+    eng = Engine(st)
+    out = eng.solve_batch(params[:0], x0[:0], make_settings(solver=W.SOLVER_SETTINGS))
+    assert out["x"].shape == (0, 8) and out["verdict"].numel() == 0
+    out = eng.solve_batch_host(params[:0], x0[:0], make_settings(solver=W.SOLVER_SETTINGS))
+    assert out["x"].shape == (0, 8)
+    eng.close()
+    # a problem without nonlinear constraints is one QP inside the SQP loop: min |x - (2,-10)|^2, x0 <= 1
+    ov = np.array([[OSQPVar("x0")], [OSQPVar("x1")]], dtype=object)
+    p = Prob()
+    for v in ov[:, 0]:
+        p.add_osqp_var(v)
+    var = Variable(ov, np.zeros((2, 1)))
+    p.add_obj_expr(E.BoundExpr(E.QuadExpr(2 * np.eye(2), np.array([[-4.0, 20.0]]), np.array([[104.0]])), var))
+    p.add_cnt_expr(E.BoundExpr(E.LEqExpr(E.AffExpr(np.array([[1.0, 0.0]]), np.zeros((1, 1))), np.ones((1, 1))), var))
+    st2, params2, x02, _ = batch.compile_batch([p])
+    ref = sqp_port.solve(st2, params2[0], x02[0], solver=W.SOLVER_SETTINGS)
+    assert _solver().solve(p, method="penalty_sqp") == ref["success"]
+    assert np.allclose(var.get_value()[:, 0], ref["x"], atol=1e-5) and np.allclose(ref["x"], [1.0, -10.0], atol=1e-4)
+    # size limits are refused with a message, not mis-solved: Jacobian rows wider than 32 entries
+    st3, params3, x03 = W.gen_qcqp(1, n=33, m=4)
+    with pytest.raises(RuntimeError, match="wider than 32"):
+        Engine(st3)
+    # the largest dense kind (n = m = 32) goes through the two-warp solver
+    st4, params4, x04 = W.gen_qcqp(2, n=32, m=32)
+    eng = Engine(st4)
+    assert eng.team == 64
+    out = eng.solve_batch(params4, x04, make_settings(solver=W.SOLVER_SETTINGS))
+    for i in range(2):
+        ref = sqp_port.solve(st4, params4[i], x04[i], solver=W.SOLVER_SETTINGS)
+        assert (int(out["verdict"][i]) == 1) == ref["success"]
+        assert np.abs(out["x"][i].cpu().numpy() - ref["x"]).max() <= 1e-4 * max(1.0, np.abs(ref["x"]).max())
+    eng.close()
