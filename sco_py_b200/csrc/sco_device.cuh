@@ -114,6 +114,22 @@ struct DevStruct {
   Layout L;
 };
 
+// By-value view of the index arrays and sizes a QP needs.  Device functions copy it (and QPW,
+// DevSettings) into locals on entry: anything read through a reference lives behind a generic pointer,
+// and since a shared-memory store may alias a generic address the compiler re-loads it after every
+// store -- measured as chains of LD.E in front of every shared access.
+struct DevIdx {
+  int n, m_lin, nnz_lin, m_nl, n_slack;
+  const int *lin_rowptr, *lin_col, *lin_cptr, *lin_centry, *lin_crow;
+  const double *lin_val;
+  const int *row_goff, *row_soff, *row_w, *row_eq, *row_gmask, *jcol_g, *pc_ptr, *pc_e, *pc_r;
+  __device__ __forceinline__ explicit DevIdx(const DevStruct &S)
+      : n(S.n), m_lin(S.m_lin), nnz_lin(S.nnz_lin), m_nl(S.m_nl), n_slack(S.n_slack), lin_rowptr(S.lin_rowptr),
+        lin_col(S.lin_col), lin_cptr(S.lin_cptr), lin_centry(S.lin_centry), lin_crow(S.lin_crow), lin_val(S.lin_val),
+        row_goff(S.row_goff), row_soff(S.row_soff), row_w(S.row_w), row_eq(S.row_eq), row_gmask(S.row_gmask),
+        jcol_g(S.jcol_g), pc_ptr(S.pc_ptr), pc_e(S.pc_e), pc_r(S.pc_r) {}
+};
+
 struct DevSettings {
   double improve_ratio_threshold, min_trust_region_size, min_approx_improve;
   double trust_shrink_ratio, trust_expand_ratio, cnt_tolerance, merit_coeff_increase_ratio;

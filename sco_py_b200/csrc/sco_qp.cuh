@@ -86,50 +86,64 @@ struct QPSolver {
 
   __device__ __forceinline__ void sync() { Team<TEAM>::sync(); }
 
-  __device__ __forceinline__ double psym(int i, int j) const {
-    if (a.closest) return i == j ? 2.0 : 0.0;
-    double v = Qg ? 0.5 * (Qg[i * n + j] + Qg[j * n + i]) : 0.0;
-    if (a.has_hq) v += 0.5 * (w.Hq[i * n + j] + w.Hq[j * n + i]);  // prob.py:348-367
-    return v;
-  }
-
-  // A' * (row-space vector) for user variable j: linear rows (vl) and penalty rows (vp; the caller
-  // folds the multiplicity kd into vp).  The bound row is added by the caller.
-  __device__ __forceinline__ double gatherAT(int j, Sh vl, Sh vp) const {
-    double acc = 0.0;
-    if (m_lin) {
-      for (int p = S.lin_cptr[j]; p < S.lin_cptr[j + 1]; p++)
-        acc += w.Als[S.lin_centry[p]] * vl[S.lin_crow[p]];
-    }
-    if (m_nl) {
-      double accp = 0.0;
-      for (int p = S.pc_ptr[j]; p < S.pc_ptr[j + 1]; p++) accp += w.Js[S.pc_e[p]] * vp[S.pc_r[p]];
-      acc += accp;
-    }
-    return acc;
-  }
-  __device__ __forceinline__ double lin_row_dot(int r, Sh v) const {
-    double acc = 0.0;
-    for (int p = S.lin_rowptr[r]; p < S.lin_rowptr[r + 1]; p++) acc += w.Als[p] * v[S.lin_col[p]];
-    return acc;
-  }
-  __device__ __forceinline__ double pen_row_dot(int i, Sh v) const {
-    const int so = S.row_soff[i], go = S.row_goff[i], wd = S.row_w[i];
-    double acc = 0.0;
-    for (int k = 0; k < wd; k++) acc += w.Js[so + k] * v[S.jcol_g[go + k]];
-    return acc;
-  }
-  __device__ __forceinline__ double pcol_norm(int j) const {  // column j of D|Psym|D * c
-    double cp = 0.0;
-    for (int i = 0; i < n; i++) cp = fmax(cp, w.D[i] * fabs(w.Sm[i * n + j]));
-    return cp * c * w.D[j];
-  }
+  // Every method starts with SCO_QP_LOCALS: by-value copies that shadow the members of the same name
+  // (see DevIdx), followed by the small helpers as lambdas over those locals.
+  //   psym(i, j)          entry of the symmetrised objective matrix (osqp_utils.py:153-163)
+  //   gatherAT(j, vl, vp) A' * (row-space vector) for user variable j: linear rows (vl) and penalty
+  //                       rows (vp; the caller folds the multiplicity kd into vp); bound row by the caller
+  //   lin_row_dot / pen_row_dot   one row of A times a variable-space vector
+  //   pcol_norm(j)        column j of c D |Psym| D
+#define SCO_QP_LOCALS                                                                                       \
+  const DevStruct &SS = this->S;                                                                            \
+  const QPW w = this->w;                                                                                    \
+  const DevIdx S(this->S);                                                                                  \
+  const DevSettings st = this->st;                                                                          \
+  const QPArgs a = this->a;                                                                                 \
+  const int tid = this->tid, n = this->n, m_lin = this->m_lin, m_nl = this->m_nl, ms = this->ms;            \
+  const double *const Qg = this->Qg;                                                                        \
+  double c = this->c, rho = this->rho;                                                                      \
+  (void)SS; (void)ms; (void)rho;                                                                            \
+  auto psym = [&](int i, int j) -> double {                                                                 \
+    if (a.closest) return i == j ? 2.0 : 0.0;                                                               \
+    double v = Qg ? 0.5 * (Qg[i * n + j] + Qg[j * n + i]) : 0.0;                                            \
+    if (a.has_hq) v += 0.5 * (w.Hq[i * n + j] + w.Hq[j * n + i]); /* prob.py:348-367 */                     \
+    return v;                                                                                               \
+  };                                                                                                        \
+  auto gatherAT = [&](int j, Sh vl, Sh vp) -> double {                                                      \
+    double acc = 0.0;                                                                                       \
+    if (m_lin)                                                                                              \
+      for (int p = S.lin_cptr[j]; p < S.lin_cptr[j + 1]; p++) acc += w.Als[S.lin_centry[p]] * vl[S.lin_crow[p]]; \
+    if (m_nl) {                                                                                             \
+      double accp = 0.0;                                                                                    \
+      for (int p = S.pc_ptr[j]; p < S.pc_ptr[j + 1]; p++) accp += w.Js[S.pc_e[p]] * vp[S.pc_r[p]];          \
+      acc += accp;                                                                                          \
+    }                                                                                                       \
+    return acc;                                                                                             \
+  };                                                                                                        \
+  auto lin_row_dot = [&](int r, Sh v) -> double {                                                           \
+    double acc = 0.0;                                                                                       \
+    for (int p = S.lin_rowptr[r]; p < S.lin_rowptr[r + 1]; p++) acc += w.Als[p] * v[S.lin_col[p]];          \
+    return acc;                                                                                             \
+  };                                                                                                        \
+  auto pen_row_dot = [&](int i, Sh v) -> double {                                                           \
+    const int so = S.row_soff[i], go = S.row_goff[i], wd = S.row_w[i];                                      \
+    double acc = 0.0;                                                                                       \
+    for (int k = 0; k < wd; k++) acc += w.Js[so + k] * v[S.jcol_g[go + k]];                                 \
+    return acc;                                                                                             \
+  };                                                                                                        \
+  auto pcol_norm = [&](int j) -> double {                                                                   \
+    double cp = 0.0;                                                                                        \
+    for (int i = 0; i < n; i++) cp = fmax(cp, w.D[i] * fabs(w.Sm[i * n + j]));                              \
+    return cp * c * w.D[j];                                                                                 \
+  };                                                                                                        \
+  (void)psym; (void)gatherAT; (void)lin_row_dot; (void)pen_row_dot; (void)pcol_norm;
 
   // ================================================================== setup
   // expects (unscaled): w.lb/w.ub bounds on x, w.bb = b, w.msk, w.xs (closest point target)
   __device__ __noinline__ void load_and_scale() {
-    const double *qg = field_ptr(S, S.q, a.prm);
-    const double *llg = field_ptr(S, S.lin_l, a.prm), *ulg = field_ptr(S, S.lin_u, a.prm);
+    SCO_QP_LOCALS
+    const double *qg = field_ptr(SS, SS.q, a.prm);
+    const double *llg = field_ptr(SS, SS.lin_l, a.prm), *ulg = field_ptr(SS, SS.lin_u, a.prm);
     for (int e = tid; e < n * n; e += TEAM) w.Sm[e] = psym(e / n, e % n);
     for (int j = tid; j < n; j += TEAM) {
       w.qh[j] = a.closest ? -2.0 * w.xs[j] : (qg ? qg[j] : 0.0) + (a.has_hq ? w.gq[j] : 0.0);
@@ -244,11 +258,14 @@ struct QPSolver {
       w.up[i] = w.Ep[i] * hi;
       w.lp[i] = S.row_eq[i] ? w.Ep[i] * hi : -OSQP_INFTY * w.Ep[i];
     }
+    this->c = c;
     sync();
   }
 
   __device__ void set_rho() {
+    SCO_QP_LOCALS
     rho = fmin(fmax(rho, OSQP_RHO_MIN), OSQP_RHO_MAX);
+    this->rho = rho;
     for (int j = tid; j < n; j += TEAM) w.rb[j] = rho_of(w.lb[j], w.ub[j], rho);
     for (int r = tid; r < m_lin; r += TEAM) w.rl[r] = rho_of(w.ll[r], w.ul[r], rho);
     for (int i = tid; i < m_nl; i += TEAM) {
@@ -262,6 +279,7 @@ struct QPSolver {
   // S = Psym^ + sigma I + A_x' R A_x - slack Schur terms, then S <- S^-1 (in place).
   // `reload`: Sm does not hold the unscaled Psym any more (rho update) -> fetch it again.
   __device__ __noinline__ void assemble_and_invert(bool reload) {
+    SCO_QP_LOCALS
     const double sigma = st.sigma;
     for (int i = tid; i < m_nl; i += TEAM) {
       const double kr = a.kd * w.rp[i];
@@ -338,6 +356,7 @@ struct QPSolver {
   // Returns a terminal status or 0.  Scratch: xt (D.*x), wp (kd*yp).  sc[] receives the scaled
   // norms needed by the rho estimate: {|Ax-z|, |z|, |Ax|, |Px+q+A'y|, |q|, |A'y|, |Px|}.
   __device__ __noinline__ int check(int approximate, double &pri_res_out, double &dua_res_out, double *sc) {
+    SCO_QP_LOCALS
     double ea = st.eps_abs, er = st.eps_rel, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
     if (approximate) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
     const double cinv = 1.0 / c;
@@ -412,6 +431,7 @@ struct QPSolver {
 
   // delta_y of the last iteration: dyl (lin), dyp (pen), dyb (x bounds), dys (slack bounds)
   __device__ __noinline__ bool primal_infeasible(double eps) {
+    SCO_QP_LOCALS
     double nv[1] = {0.0}, lhs[1] = {0.0};
     for (int r = tid; r < m_lin; r += TEAM) {
       const double dy = proj_dy(w.dyl[r], w.ll[r], w.ul[r]);
@@ -465,6 +485,7 @@ struct QPSolver {
 
   // delta_x of the last iteration: dxv (user variables), dss (slacks)
   __device__ __noinline__ bool dual_infeasible(double eps) {
+    SCO_QP_LOCALS
     double nv[1] = {0.0}, qd[1] = {0.0};
     for (int j = tid; j < n; j += TEAM) {
       nv[0] = fmax(nv[0], fabs(w.D[j] * w.dxv[j]));
@@ -530,6 +551,7 @@ struct QPSolver {
   // On return w.x (user variables) and w.s (slacks) hold the UNSCALED solution.
   // generic shared-memory ADMM loop; returns the status (0 = max_iter reached without a verdict)
   __device__ __noinline__ int generic_loop(int &iter_out, bool &checked_out, QPResult &res) {
+    SCO_QP_LOCALS
     const double sigma = st.sigma, alpha = st.alpha, oma = 1.0 - st.alpha;
     for (int j = tid; j < n; j += TEAM) { w.x[j] = 0.0; w.zb[j] = 0.0; w.yb[j] = 0.0; }
     for (int r = tid; r < m_lin; r += TEAM) { w.zl[r] = 0.0; w.yl[r] = 0.0; }
@@ -650,8 +672,9 @@ struct QPSolver {
           double rn = rho * sqrt(pri / (dua + 1e-10));
           rn = fmin(fmax(rn, OSQP_RHO_MIN), OSQP_RHO_MAX);
           if (rn > rho * 5.0 || rn < rho / 5.0) {
-            rho = rn;
+            this->rho = rn;
             set_rho();
+            rho = this->rho;
             assemble_and_invert(true);
           }
         }
