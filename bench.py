@@ -297,7 +297,8 @@ def run_b200_arm(args):
     outs = run_steps(args.steps)
     e1.record(cur)
     barrier()
-    ms_total = reduce_max(e0.elapsed_time(e1))
+    ms_local = e0.elapsed_time(e1)
+    ms_total = reduce_max(ms_local)
     clocks = sampler.stop() if rank == 0 else None
     out = outs[-1]
     verdict = out["verdict"].cpu().numpy()
@@ -307,6 +308,14 @@ def run_b200_arm(args):
             raise SystemExit("bench.py: two steps over the same batch disagree")
     converged = reduce_sum(float((verdict == 1).sum()))
     value = converged * args.steps / (ms_total * 1e-3)
+    # per-rank view of the tail: every rank's own device time and its longest problem (the step ends
+    # when the rank that holds the longest problems is done)
+    per_rank = [[ms_local / args.steps, float(stats[:, 2].max()), float(stats[:, 2].astype(np.float64).sum())]]
+    if world > 1:
+        t = torch.tensor(per_rank[0], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [a.cpu().tolist() for a in allt]
 
     # ---- end-to-end leg: host buffers through the C ABI (sco_solve_batch_host_async), the H2D copy
     # of every step's inputs and the D2H copy of its results inside the timed region, same pipelining
@@ -414,6 +423,9 @@ def run_b200_arm(args):
                    "verdict_counts": {str(k): int((verdict == k).sum()) for k in (-1, 0, 1)},
                    "mean_sqp_iters": float(stats[:, 0].mean()), "mean_qp_solves": float(stats[:, 1].mean()),
                    "mean_admm_iters": float(stats[:, 2].mean()), "max_admm_iters": int(stats[:, 2].max()),
+                   "per_rank": [{"rank": r, "ms_per_step": round(v[0], 1), "max_admm_iters": int(v[1]),
+                                 "busy_fraction": round(v[0] / ms_step, 3), "total_admm_iters": int(v[2])}
+                                for r, v in enumerate(per_rank)],
                    "team": eng.team, "smem_bytes": eng.smem_bytes, "ctas_per_sm": eng.occupancy,
                    "gen_seconds": t_gen},
     }
@@ -435,7 +447,7 @@ def main():
     ap.add_argument("--config", default="qcqp", choices=["qcqp", "point_robot", "arm"])
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the steps are pipelined over (1..4)")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the steps are pipelined over (1..4)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU sample (default: two per core)")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
