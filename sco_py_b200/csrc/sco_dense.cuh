@@ -719,6 +719,32 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
     __syncthreads();
     int cert;
     status = dense_test<NP, MP>(sb, rowwarp, lane, u0, u1, u2, lo, hi, X, false, res.pri_res, res.dua_res, cert);
+#ifdef SCO_SKIP_PROBE
+    {  // experiment: how often would a lane-local lower bound of the primal residual already decide "not converged"?
+      const double r0p = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 5)), r1p = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 6));
+      double plb, vloc, dummy = 0.0;
+      if (rowwarp) {
+        const double axs = u2 * X.s;
+        plb = fabs((axs - X.zs) * r1p);
+        vloc = max_nn(fabs(X.z0 * r0p), max_nn(fabs(X.zs * r1p), fabs(axs * r1p)));
+      } else {
+        const double ax = u1 * X.p0;
+        plb = fabs((ax - X.z0) * r0p);
+        vloc = max_nn(fabs(X.z0 * r0p), fabs(ax * r0p));
+      }
+      double dlb = 0.0;
+      if (rowwarp) dlb = fabs((u0 + (lo * X.y0 + u2 * X.ys)) * lds_f64(dense_la<NP, MP>(sb, true, lane, 7))) * dense_sc<NP, MP>(sb, 5);
+      dense_team2<NP, MP>(sb, rowwarp, lane, dlb, dummy);
+      dense_team2<NP, MP>(sb, rowwarp, lane, plb, dummy);
+      dense_team2<NP, MP>(sb, rowwarp, lane, vloc, dummy);
+      if (status == 0 && (dlb >= 2.0 * dense_sc<NP, MP>(sb, 0))) res.cyc_c[4] += 1;  // slack-column dual bound alone
+      const double ep = (dense_sc<NP, MP>(sb, 0) + dense_sc<NP, MP>(sb, 1) * vloc) / (1.0 - dense_sc<NP, MP>(sb, 1)) * (1.0 + 1e-12);
+      res.cyc_c[0] += 1;                       // tests
+      if (status == 0) res.cyc_c[1] += 1;      // failing tests
+      if (status == 0 && (plb >= ep || dlb >= 2.0 * dense_sc<NP, MP>(sb, 0))) res.cyc_c[2] += 1;  // ... that the bounds decide
+      if (status != 0 && plb >= ep) res.cyc_c[3] += 1;  // must stay 0 (the bound is rigorous)
+    }
+#endif
     if (status != 0) break;
     if (cert) {
       dense_spill<NP, MP>(sb, rowwarp, lane, X);
