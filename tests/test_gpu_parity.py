@@ -202,3 +202,32 @@ def test_dense_register_path_matches_generic_path(engines):
     same = va == vg
     dx = np.abs(a["x"].cpu().numpy() - g["x"].cpu().numpy()).max(axis=1)
     assert np.quantile(dx[same], 0.9) <= 1e-4
+
+
+def test_adaptive_rho_reaches_the_same_qp_optimum(engines):
+    """`adaptive_rho=True` is selectable through Solver.solve (solver.py:39).  Upstream OSQP picks the
+    adaptation interval from wall-clock setup time, so iteration counts are not comparable; the QP
+    optimum is: same status class and x to 1e-5 against the oracle run with
+    the same flag, on the generic path and on a dense structure (which falls back to it)."""
+    for name in ("qcqp", "point_robot"):
+        eng, st, params, x0 = engines[name]
+        B = x0.shape[0]
+        f, J, b, _ = eng.convexify(params, x0)
+        Jn, bn = J.cpu().numpy(), b.cpu().numpy()
+        lbx, ubx = x0 - 0.3, x0 + 0.3
+        s = _settings()
+        s.osqp_adaptive_rho = 1
+        xq, status, iters = eng.qp_solve(params, s, J=J, b=b, lbx=lbx, ubx=ubx, pi=np.full(B, 10.0),
+                                         kdup=np.full(B, 2, np.int32))
+        xq, status = xq.cpu().numpy(), status.cpu().numpy()
+        for i in range(min(B, 3)):
+            Jd = helpers.split_J(st, Jn[i])
+            bl, r0 = [], 0
+            for blk in st.blocks:
+                bl.append(bn[i, r0:r0 + blk.m])
+                r0 += blk.m
+            masks = [np.ones_like(Jb, dtype=bool) for Jb in Jd]
+            P, q, A, l, u = helpers.expand_qp(st, params[i], Jd, bl, masks, lbx[i], ubx[i], 10.0, 2)
+            res = helpers.oracle_qp(P, q, A, l, u, adaptive_rho=True)
+            assert status[i] in (1, 2) and res.info.status_val in (1, 2), (name, i, status[i], res.info.status_val)
+            assert np.abs(xq[i] - res.x).max() <= 1e-5 * max(1.0, np.abs(res.x).max()), (name, i)
