@@ -95,7 +95,20 @@ struct QPSolver {
   //   pcol_norm(j)        column j of c D |Psym| D
 #define SCO_QP_LOCALS                                                                                       \
   const DevStruct &SS = this->S;                                                                            \
-  const QPW w = this->w;                                                                                    \
+  const QPW w = this->w; /* offsets as individual scalars: registers, not a struct in local memory */        \
+  const Sh W_Js = w.Js, W_Sm = w.Sm, W_Als = w.Als, W_x = w.x, W_xt = w.xt, W_xt2 = w.xt2,                  \
+      W_qh = w.qh, W_D = w.D, W_bx = w.bx, W_rb = w.rb, W_lb = w.lb, W_ub = w.ub, W_zb = w.zb,              \
+      W_yb = w.yb, W_Eb = w.Eb, W_dxv = w.dxv, W_dyb = w.dyb, W_xs = w.xs, W_El = w.El,                     \
+      W_rl = w.rl, W_ll = w.ll, W_ul = w.ul, W_zl = w.zl, W_yl = w.yl, W_wl = w.wl, W_dyl = w.dyl,          \
+      W_Ep = w.Ep, W_rp = w.rp, W_lp = w.lp, W_up = w.up, W_zp = w.zp, W_yp = w.yp, W_wp = w.wp,            \
+      W_bb = w.bb, W_fv = w.fv, W_dyp = w.dyp, W_s = w.s, W_Ds = w.Ds, W_sl = w.sl, W_bs = w.bs,            \
+      W_zs = w.zs, W_ys = w.ys, W_Es = w.Es, W_gs = w.gs, W_hs = w.hs, W_rs = w.rs, W_dss = w.dss,          \
+      W_dys = w.dys, W_Minv = w.Minv, W_red = w.red, W_stage = w.stage, W_Hq = w.Hq, W_gq = w.gq,           \
+      W_xc = w.xc;                                                                                          \
+  const ShU32 W_msk = w.msk;                                                                                \
+  (void)W_msk; (void)W_Js; (void)W_Sm; (void)W_Als; (void)W_x; (void)W_xt; (void)W_xt2; (void)W_qh; (void)W_D; (void)W_bx; (void)W_rb; (void)W_lb; (void)W_ub; (void)W_zb; (void)W_yb; (void)W_Eb; (void)W_dxv; (void)W_dyb; (void)W_xs; (void)W_El; (void)W_rl;\
+  (void)W_ll; (void)W_ul; (void)W_zl; (void)W_yl; (void)W_wl; (void)W_dyl; (void)W_Ep; (void)W_rp; (void)W_lp; (void)W_up; (void)W_zp; (void)W_yp; (void)W_wp; (void)W_bb; (void)W_fv; (void)W_dyp; (void)W_s; (void)W_Ds; (void)W_sl; (void)W_bs;\
+  (void)W_zs; (void)W_ys; (void)W_Es; (void)W_gs; (void)W_hs; (void)W_rs; (void)W_dss; (void)W_dys; (void)W_Minv; (void)W_red; (void)W_stage; (void)W_Hq; (void)W_gq; (void)W_xc;\
   const DevIdx S(this->S);                                                                                  \
   const DevSettings st = this->st;                                                                          \
   const QPArgs a = this->a;                                                                                 \
@@ -106,61 +119,61 @@ struct QPSolver {
   auto psym = [&](int i, int j) -> double {                                                                 \
     if (a.closest) return i == j ? 2.0 : 0.0;                                                               \
     double v = Qg ? 0.5 * (Qg[i * n + j] + Qg[j * n + i]) : 0.0;                                            \
-    if (a.has_hq) v += 0.5 * (w.Hq[i * n + j] + w.Hq[j * n + i]); /* prob.py:348-367 */                     \
+    if (a.has_hq) v += 0.5 * (W_Hq[i * n + j] + W_Hq[j * n + i]); /* prob.py:348-367 */                     \
     return v;                                                                                               \
   };                                                                                                        \
   auto gatherAT = [&](int j, Sh vl, Sh vp) -> double {                                                      \
     double acc = 0.0;                                                                                       \
     if (m_lin)                                                                                              \
-      for (int p = S.lin_cptr[j]; p < S.lin_cptr[j + 1]; p++) acc += w.Als[S.lin_centry[p]] * vl[S.lin_crow[p]]; \
+      for (int p = __ldg(S.lin_cptr + (j)); p < __ldg(S.lin_cptr + (j + 1)); p++) acc += W_Als[__ldg(S.lin_centry + (p))] * vl[__ldg(S.lin_crow + (p))]; \
     if (m_nl) {                                                                                             \
       double accp = 0.0;                                                                                    \
-      for (int p = S.pc_ptr[j]; p < S.pc_ptr[j + 1]; p++) accp += w.Js[S.pc_e[p]] * vp[S.pc_r[p]];          \
+      for (int p = __ldg(S.pc_ptr + (j)); p < __ldg(S.pc_ptr + (j + 1)); p++) accp += W_Js[__ldg(S.pc_e + (p))] * vp[__ldg(S.pc_r + (p))];          \
       acc += accp;                                                                                          \
     }                                                                                                       \
     return acc;                                                                                             \
   };                                                                                                        \
   auto lin_row_dot = [&](int r, Sh v) -> double {                                                           \
     double acc = 0.0;                                                                                       \
-    for (int p = S.lin_rowptr[r]; p < S.lin_rowptr[r + 1]; p++) acc += w.Als[p] * v[S.lin_col[p]];          \
+    for (int p = __ldg(S.lin_rowptr + (r)); p < __ldg(S.lin_rowptr + (r + 1)); p++) acc += W_Als[p] * v[__ldg(S.lin_col + (p))];          \
     return acc;                                                                                             \
   };                                                                                                        \
   auto pen_row_dot = [&](int i, Sh v) -> double {                                                           \
-    const int so = S.row_soff[i], go = S.row_goff[i], wd = S.row_w[i];                                      \
+    const int so = __ldg(S.row_soff + (i)), go = __ldg(S.row_goff + (i)), wd = __ldg(S.row_w + (i));                                      \
     double acc = 0.0;                                                                                       \
-    for (int k = 0; k < wd; k++) acc += w.Js[so + k] * v[S.jcol_g[go + k]];                                 \
+    for (int k = 0; k < wd; k++) acc += W_Js[so + k] * v[__ldg(S.jcol_g + (go + k))];                                 \
     return acc;                                                                                             \
   };                                                                                                        \
   auto pcol_norm = [&](int j) -> double {                                                                   \
     double cp = 0.0;                                                                                        \
-    for (int i = 0; i < n; i++) cp = fmax(cp, w.D[i] * fabs(w.Sm[i * n + j]));                              \
-    return cp * c * w.D[j];                                                                                 \
+    for (int i = 0; i < n; i++) cp = fmax(cp, W_D[i] * fabs(W_Sm[i * n + j]));                              \
+    return cp * c * W_D[j];                                                                                 \
   };                                                                                                        \
   (void)psym; (void)gatherAT; (void)lin_row_dot; (void)pen_row_dot; (void)pcol_norm;
 
   // ================================================================== setup
-  // expects (unscaled): w.lb/w.ub bounds on x, w.bb = b, w.msk, w.xs (closest point target)
+  // expects (unscaled): W_lb/W_ub bounds on x, W_bb = b, W_msk, W_xs (closest point target)
   __device__ __noinline__ void load_and_scale() {
     SCO_QP_LOCALS
     const double *qg = field_ptr(SS, SS.q, a.prm);
     const double *llg = field_ptr(SS, SS.lin_l, a.prm), *ulg = field_ptr(SS, SS.lin_u, a.prm);
-    for (int e = tid; e < n * n; e += TEAM) w.Sm[e] = psym(e / n, e % n);
+    for (int e = tid; e < n * n; e += TEAM) W_Sm[e] = psym(e / n, e % n);
     for (int j = tid; j < n; j += TEAM) {
-      w.qh[j] = a.closest ? -2.0 * w.xs[j] : (qg ? qg[j] : 0.0) + (a.has_hq ? w.gq[j] : 0.0);
-      w.D[j] = 1.0;
-      w.bx[j] = 1.0;
-      w.Eb[j] = 1.0;
+      W_qh[j] = a.closest ? -2.0 * W_xs[j] : (qg ? qg[j] : 0.0) + (a.has_hq ? W_gq[j] : 0.0);
+      W_D[j] = 1.0;
+      W_bx[j] = 1.0;
+      W_Eb[j] = 1.0;
     }
-    for (int e = tid; e < S.nnz_lin; e += TEAM) w.Als[e] = S.lin_val[e];
-    for (int r = tid; r < m_lin; r += TEAM) w.El[r] = 1.0;
+    for (int e = tid; e < S.nnz_lin; e += TEAM) W_Als[e] = __ldg(S.lin_val + (e));
+    for (int r = tid; r < m_lin; r += TEAM) W_El[r] = 1.0;
     for (int i = tid; i < m_nl; i += TEAM) {
-      const int so = S.row_soff[i], go = S.row_goff[i], wd = S.row_w[i];
-      const uint32_t mk = w.msk[i];
-      for (int k = 0; k < wd; k++) w.Js[so + k] = ((mk >> k) & 1u) ? a.Jg[go + k] : 0.0;
-      w.Ep[i] = 1.0;
-      w.sl[i] = -1.0; w.bs[i] = 1.0; w.Ds[i] = 1.0; w.Es[i] = 1.0;
-      if (S.row_eq[i]) {
-        w.sl[ms + i] = 1.0; w.bs[ms + i] = 1.0; w.Ds[ms + i] = 1.0; w.Es[ms + i] = 1.0;
+      const int so = __ldg(S.row_soff + (i)), go = __ldg(S.row_goff + (i)), wd = __ldg(S.row_w + (i));
+      const uint32_t mk = W_msk[i];
+      for (int k = 0; k < wd; k++) W_Js[so + k] = ((mk >> k) & 1u) ? a.Jg[go + k] : 0.0;
+      W_Ep[i] = 1.0;
+      W_sl[i] = -1.0; W_bs[i] = 1.0; W_Ds[i] = 1.0; W_Es[i] = 1.0;
+      if (__ldg(S.row_eq + (i))) {
+        W_sl[ms + i] = 1.0; W_bs[ms + i] = 1.0; W_Ds[ms + i] = 1.0; W_Es[ms + i] = 1.0;
       }
     }
     c = 1.0;
@@ -170,93 +183,93 @@ struct QPSolver {
     for (int it = 0; it < st.scaling; it++) {
       for (int j = tid; j < n; j += TEAM) {
         const double cp = pcol_norm(j);
-        double ca = fabs(w.bx[j]);
+        double ca = fabs(W_bx[j]);
         if (m_lin)
-          for (int p = S.lin_cptr[j]; p < S.lin_cptr[j + 1]; p++)
-            ca = fmax(ca, fabs(w.Als[S.lin_centry[p]]));
+          for (int p = __ldg(S.lin_cptr + (j)); p < __ldg(S.lin_cptr + (j + 1)); p++)
+            ca = fmax(ca, fabs(W_Als[__ldg(S.lin_centry + (p))]));
         if (m_nl)
-          for (int p = S.pc_ptr[j]; p < S.pc_ptr[j + 1]; p++) ca = fmax(ca, fabs(w.Js[S.pc_e[p]]));
-        w.xt[j] = 1.0 / sqrt(limit_scaling(fmax(cp, ca)));
-        w.xt2[j] = 1.0 / sqrt(limit_scaling(fabs(w.bx[j])));
+          for (int p = __ldg(S.pc_ptr + (j)); p < __ldg(S.pc_ptr + (j + 1)); p++) ca = fmax(ca, fabs(W_Js[__ldg(S.pc_e + (p))]));
+        W_xt[j] = 1.0 / sqrt(limit_scaling(fmax(cp, ca)));
+        W_xt2[j] = 1.0 / sqrt(limit_scaling(fabs(W_bx[j])));
       }
       for (int r = tid; r < m_lin; r += TEAM) {
         double rn = 0.0;
-        for (int p = S.lin_rowptr[r]; p < S.lin_rowptr[r + 1]; p++) rn = fmax(rn, fabs(w.Als[p]));
-        w.wl[r] = 1.0 / sqrt(limit_scaling(rn));
+        for (int p = __ldg(S.lin_rowptr + (r)); p < __ldg(S.lin_rowptr + (r + 1)); p++) rn = fmax(rn, fabs(W_Als[p]));
+        W_wl[r] = 1.0 / sqrt(limit_scaling(rn));
       }
       for (int i = tid; i < m_nl; i += TEAM) {
-        const int so = S.row_soff[i], wd = S.row_w[i], eq = S.row_eq[i];
-        double rn = fabs(w.sl[i]);
-        if (eq) rn = fmax(rn, fabs(w.sl[ms + i]));
-        for (int k = 0; k < wd; k++) rn = fmax(rn, fabs(w.Js[so + k]));
-        w.wp[i] = 1.0 / sqrt(limit_scaling(rn));
+        const int so = __ldg(S.row_soff + (i)), wd = __ldg(S.row_w + (i)), eq = __ldg(S.row_eq + (i));
+        double rn = fabs(W_sl[i]);
+        if (eq) rn = fmax(rn, fabs(W_sl[ms + i]));
+        for (int k = 0; k < wd; k++) rn = fmax(rn, fabs(W_Js[so + k]));
+        W_wp[i] = 1.0 / sqrt(limit_scaling(rn));
         for (int k2 = 0; k2 <= eq; k2++) {
           const int si = k2 * ms + i;
-          w.gs[si] = 1.0 / sqrt(limit_scaling(fmax(fabs(w.sl[si]), fabs(w.bs[si]))));
-          w.dys[si] = 1.0 / sqrt(limit_scaling(fabs(w.bs[si])));
+          W_gs[si] = 1.0 / sqrt(limit_scaling(fmax(fabs(W_sl[si]), fabs(W_bs[si]))));
+          W_dys[si] = 1.0 / sqrt(limit_scaling(fabs(W_bs[si])));
         }
       }
       sync();
       for (int r = tid; r < m_lin; r += TEAM) {
-        const double er = w.wl[r];
-        for (int p = S.lin_rowptr[r]; p < S.lin_rowptr[r + 1]; p++)
-          w.Als[p] *= er * w.xt[S.lin_col[p]];
-        w.El[r] *= er;
+        const double er = W_wl[r];
+        for (int p = __ldg(S.lin_rowptr + (r)); p < __ldg(S.lin_rowptr + (r + 1)); p++)
+          W_Als[p] *= er * W_xt[__ldg(S.lin_col + (p))];
+        W_El[r] *= er;
       }
       for (int i = tid; i < m_nl; i += TEAM) {
-        const int so = S.row_soff[i], go = S.row_goff[i], wd = S.row_w[i], eq = S.row_eq[i];
-        const double er = w.wp[i];
-        for (int k = 0; k < wd; k++) w.Js[so + k] *= er * w.xt[S.jcol_g[go + k]];
-        w.Ep[i] *= er;
+        const int so = __ldg(S.row_soff + (i)), go = __ldg(S.row_goff + (i)), wd = __ldg(S.row_w + (i)), eq = __ldg(S.row_eq + (i));
+        const double er = W_wp[i];
+        for (int k = 0; k < wd; k++) W_Js[so + k] *= er * W_xt[__ldg(S.jcol_g + (go + k))];
+        W_Ep[i] *= er;
         for (int k2 = 0; k2 <= eq; k2++) {
           const int si = k2 * ms + i;
-          w.sl[si] *= er * w.gs[si];
-          w.bs[si] *= w.dys[si] * w.gs[si];
-          w.Ds[si] *= w.gs[si];
-          w.Es[si] *= w.dys[si];
+          W_sl[si] *= er * W_gs[si];
+          W_bs[si] *= W_dys[si] * W_gs[si];
+          W_Ds[si] *= W_gs[si];
+          W_Es[si] *= W_dys[si];
         }
       }
       sync();  // column data of Js / Als final before D changes (pcol_norm below reads D only)
       for (int j = tid; j < n; j += TEAM) {
-        w.bx[j] *= w.xt2[j] * w.xt[j];
-        w.Eb[j] *= w.xt2[j];
-        w.qh[j] *= w.xt[j];
-        w.D[j] *= w.xt[j];
+        W_bx[j] *= W_xt2[j] * W_xt[j];
+        W_Eb[j] *= W_xt2[j];
+        W_qh[j] *= W_xt[j];
+        W_D[j] *= W_xt[j];
       }
       sync();
       // cost normalisation
       double vs[1] = {0.0}, vm[1] = {0.0};
       for (int j = tid; j < n; j += TEAM) {
         vs[0] += pcol_norm(j);
-        vm[0] = fmax(vm[0], fabs(w.qh[j]));
+        vm[0] = fmax(vm[0], fabs(W_qh[j]));
       }
       if (m_nl) {
         const double cq = fabs(c * a.pi);
         for (int i = tid; i < m_nl; i += TEAM)
-          for (int k2 = 0; k2 <= S.row_eq[i]; k2++) vm[0] = fmax(vm[0], cq * w.Ds[k2 * ms + i]);
+          for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) vm[0] = fmax(vm[0], cq * W_Ds[k2 * ms + i]);
       }
-      Team<TEAM>::reduce_sum(vs, w.red);
-      Team<TEAM>::reduce_max(vm, w.red);
+      Team<TEAM>::reduce_sum(vs, W_red);
+      Team<TEAM>::reduce_max(vm, W_red);
       const double mean = vs[0] / (double)nq;
       const double ct = 1.0 / limit_scaling(fmax(mean, limit_scaling(vm[0])));
-      for (int j = tid; j < n; j += TEAM) w.qh[j] *= ct;
+      for (int j = tid; j < n; j += TEAM) W_qh[j] *= ct;
       c *= ct;
       sync();
     }
     // scaled bounds
     for (int j = tid; j < n; j += TEAM) {
-      const double eb = w.Eb[j];
-      w.lb[j] = eb * fmax(w.lb[j], -OSQP_INFTY);
-      w.ub[j] = eb * fmin(w.ub[j], OSQP_INFTY);
+      const double eb = W_Eb[j];
+      W_lb[j] = eb * fmax(W_lb[j], -OSQP_INFTY);
+      W_ub[j] = eb * fmin(W_ub[j], OSQP_INFTY);
     }
     for (int r = tid; r < m_lin; r += TEAM) {
-      w.ll[r] = w.El[r] * fmax(llg ? llg[r] : 0.0, -OSQP_INFTY);
-      w.ul[r] = w.El[r] * fmin(ulg ? ulg[r] : 0.0, OSQP_INFTY);
+      W_ll[r] = W_El[r] * fmax(llg ? llg[r] : 0.0, -OSQP_INFTY);
+      W_ul[r] = W_El[r] * fmin(ulg ? ulg[r] : 0.0, OSQP_INFTY);
     }
     for (int i = tid; i < m_nl; i += TEAM) {
-      const double hi = clampd(-w.bb[i], -OSQP_INFTY, OSQP_INFTY);
-      w.up[i] = w.Ep[i] * hi;
-      w.lp[i] = S.row_eq[i] ? w.Ep[i] * hi : -OSQP_INFTY * w.Ep[i];
+      const double hi = clampd(-W_bb[i], -OSQP_INFTY, OSQP_INFTY);
+      W_up[i] = W_Ep[i] * hi;
+      W_lp[i] = __ldg(S.row_eq + (i)) ? W_Ep[i] * hi : -OSQP_INFTY * W_Ep[i];
     }
     this->c = c;
     sync();
@@ -266,12 +279,12 @@ struct QPSolver {
     SCO_QP_LOCALS
     rho = fmin(fmax(rho, OSQP_RHO_MIN), OSQP_RHO_MAX);
     this->rho = rho;
-    for (int j = tid; j < n; j += TEAM) w.rb[j] = rho_of(w.lb[j], w.ub[j], rho);
-    for (int r = tid; r < m_lin; r += TEAM) w.rl[r] = rho_of(w.ll[r], w.ul[r], rho);
+    for (int j = tid; j < n; j += TEAM) W_rb[j] = rho_of(W_lb[j], W_ub[j], rho);
+    for (int r = tid; r < m_lin; r += TEAM) W_rl[r] = rho_of(W_ll[r], W_ul[r], rho);
     for (int i = tid; i < m_nl; i += TEAM) {
-      w.rp[i] = rho_of(w.lp[i], w.up[i], rho);
-      for (int k2 = 0; k2 <= S.row_eq[i]; k2++)
-        w.rs[k2 * ms + i] = rho_of(0.0, OSQP_INFTY * w.Es[k2 * ms + i], rho);
+      W_rp[i] = rho_of(W_lp[i], W_up[i], rho);
+      for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++)
+        W_rs[k2 * ms + i] = rho_of(0.0, OSQP_INFTY * W_Es[k2 * ms + i], rho);
     }
     sync();
   }
@@ -282,71 +295,71 @@ struct QPSolver {
     SCO_QP_LOCALS
     const double sigma = st.sigma;
     for (int i = tid; i < m_nl; i += TEAM) {
-      const double kr = a.kd * w.rp[i];
-      const double s1 = w.sl[i], b1 = w.bs[i];
-      const double m11 = sigma + kr * s1 * s1 + w.rs[i] * b1 * b1;
+      const double kr = a.kd * W_rp[i];
+      const double s1 = W_sl[i], b1 = W_bs[i];
+      const double m11 = sigma + kr * s1 * s1 + W_rs[i] * b1 * b1;
       double coef;
-      if (S.row_eq[i]) {
-        const double s2 = w.sl[ms + i], b2 = w.bs[ms + i];
-        const double m22 = sigma + kr * s2 * s2 + w.rs[ms + i] * b2 * b2;
+      if (__ldg(S.row_eq + (i))) {
+        const double s2 = W_sl[ms + i], b2 = W_bs[ms + i];
+        const double m22 = sigma + kr * s2 * s2 + W_rs[ms + i] * b2 * b2;
         const double m12 = kr * s1 * s2;
         const double det = m11 * m22 - m12 * m12;
         const double i11 = m22 / det, i22 = m11 / det, i12 = -m12 / det;
-        w.Minv[3 * i] = i11; w.Minv[3 * i + 1] = i12; w.Minv[3 * i + 2] = i22;
+        W_Minv[3 * i] = i11; W_Minv[3 * i + 1] = i12; W_Minv[3 * i + 2] = i22;
         const double h1 = kr * (i11 * s1 + i12 * s2), h2 = kr * (i12 * s1 + i22 * s2);
-        w.hs[i] = h1; w.hs[ms + i] = h2;
+        W_hs[i] = h1; W_hs[ms + i] = h2;
         coef = kr - kr * (s1 * h1 + s2 * h2);
       } else {
         const double i11 = 1.0 / m11;
-        w.Minv[3 * i] = i11; w.Minv[3 * i + 1] = 0.0; w.Minv[3 * i + 2] = 0.0;
+        W_Minv[3 * i] = i11; W_Minv[3 * i + 1] = 0.0; W_Minv[3 * i + 2] = 0.0;
         const double h1 = kr * i11 * s1;
-        w.hs[i] = h1;
+        W_hs[i] = h1;
         coef = kr - kr * s1 * h1;
       }
-      w.wp[i] = coef;
+      W_wp[i] = coef;
     }
     for (int e = tid; e < n * n; e += TEAM) {
       const int i = e / n, j = e % n;
-      const double pv = reload ? psym(i, j) : w.Sm[e];
-      double v = c * w.D[i] * pv * w.D[j];
-      if (i == j) v += sigma + w.rb[j] * w.bx[j] * w.bx[j];
-      w.Sm[e] = v;
+      const double pv = reload ? psym(i, j) : W_Sm[e];
+      double v = c * W_D[i] * pv * W_D[j];
+      if (i == j) v += sigma + W_rb[j] * W_bx[j] * W_bx[j];
+      W_Sm[e] = v;
     }
     sync();
     for (int j = tid; j < n; j += TEAM) {
       if (m_lin) {
-        for (int p = S.lin_cptr[j]; p < S.lin_cptr[j + 1]; p++) {
-          const int r = S.lin_crow[p];
-          const double f = w.rl[r] * w.Als[S.lin_centry[p]];
-          for (int q2 = S.lin_rowptr[r]; q2 < S.lin_rowptr[r + 1]; q2++)
-            w.Sm[S.lin_col[q2] * n + j] += f * w.Als[q2];
+        for (int p = __ldg(S.lin_cptr + (j)); p < __ldg(S.lin_cptr + (j + 1)); p++) {
+          const int r = __ldg(S.lin_crow + (p));
+          const double f = W_rl[r] * W_Als[__ldg(S.lin_centry + (p))];
+          for (int q2 = __ldg(S.lin_rowptr + (r)); q2 < __ldg(S.lin_rowptr + (r + 1)); q2++)
+            W_Sm[__ldg(S.lin_col + (q2)) * n + j] += f * W_Als[q2];
         }
       }
       if (m_nl) {
-        for (int p = S.pc_ptr[j]; p < S.pc_ptr[j + 1]; p++) {
-          const int r = S.pc_r[p];
-          const double f = w.wp[r] * w.Js[S.pc_e[p]];
-          const int so = S.row_soff[r], go = S.row_goff[r], wd = S.row_w[r];
-          for (int k = 0; k < wd; k++) w.Sm[S.jcol_g[go + k] * n + j] += f * w.Js[so + k];
+        for (int p = __ldg(S.pc_ptr + (j)); p < __ldg(S.pc_ptr + (j + 1)); p++) {
+          const int r = __ldg(S.pc_r + (p));
+          const double f = W_wp[r] * W_Js[__ldg(S.pc_e + (p))];
+          const int so = __ldg(S.row_soff + (r)), go = __ldg(S.row_goff + (r)), wd = __ldg(S.row_w + (r));
+          for (int k = 0; k < wd; k++) W_Sm[__ldg(S.jcol_g + (go + k)) * n + j] += f * W_Js[so + k];
         }
       }
     }
     sync();
     // in-place Gauss-Jordan inverse (S is SPD: no pivoting).  xt = pivot row, xt2 = pivot column
     for (int k = 0; k < n; k++) {
-      const double d = 1.0 / w.Sm[k * n + k];
+      const double d = 1.0 / W_Sm[k * n + k];
       for (int j = tid; j < n; j += TEAM) {
-        w.xt[j] = w.Sm[k * n + j] * d;
-        w.xt2[j] = w.Sm[j * n + k];
+        W_xt[j] = W_Sm[k * n + j] * d;
+        W_xt2[j] = W_Sm[j * n + k];
       }
       sync();
       for (int e = tid; e < n * n; e += TEAM) {
         const int i = e / n, j = e % n;
         double v;
-        if (i == k) v = (j == k) ? d : w.xt[j];
-        else if (j == k) v = -w.xt2[i] * d;
-        else v = w.Sm[e] - w.xt2[i] * w.xt[j];
-        w.Sm[e] = v;
+        if (i == k) v = (j == k) ? d : W_xt[j];
+        else if (j == k) v = -W_xt2[i] * d;
+        else v = W_Sm[e] - W_xt2[i] * W_xt[j];
+        W_Sm[e] = v;
       }
       sync();
     }
@@ -364,53 +377,53 @@ struct QPSolver {
     double v[7] = {0, 0, 0, 0, 0, 0, 0};
     double u[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int r = tid; r < m_lin; r += TEAM) {
-      const double ax = lin_row_dot(r, w.x), ei = 1.0 / w.El[r], z = w.zl[r];
+      const double ax = lin_row_dot(r, W_x), ei = 1.0 / W_El[r], z = W_zl[r];
       v[0] = fmax(v[0], fabs((ax - z) * ei)); v[1] = fmax(v[1], fabs(z * ei)); v[2] = fmax(v[2], fabs(ax * ei));
       u[0] = fmax(u[0], fabs(ax - z)); u[1] = fmax(u[1], fabs(z)); u[2] = fmax(u[2], fabs(ax));
     }
     for (int i = tid; i < m_nl; i += TEAM) {
-      const int eq = S.row_eq[i];
-      double ax = pen_row_dot(i, w.x) + w.sl[i] * w.s[i];
-      if (eq) ax += w.sl[ms + i] * w.s[ms + i];
-      double ei = 1.0 / w.Ep[i], z = w.zp[i];
+      const int eq = __ldg(S.row_eq + (i));
+      double ax = pen_row_dot(i, W_x) + W_sl[i] * W_s[i];
+      if (eq) ax += W_sl[ms + i] * W_s[ms + i];
+      double ei = 1.0 / W_Ep[i], z = W_zp[i];
       v[0] = fmax(v[0], fabs((ax - z) * ei)); v[1] = fmax(v[1], fabs(z * ei)); v[2] = fmax(v[2], fabs(ax * ei));
       u[0] = fmax(u[0], fabs(ax - z)); u[1] = fmax(u[1], fabs(z)); u[2] = fmax(u[2], fabs(ax));
       for (int k2 = 0; k2 <= eq; k2++) {
         const int si = k2 * ms + i;
-        const double axs = w.bs[si] * w.s[si];
-        ei = 1.0 / w.Es[si]; z = w.zs[si];
+        const double axs = W_bs[si] * W_s[si];
+        ei = 1.0 / W_Es[si]; z = W_zs[si];
         v[0] = fmax(v[0], fabs((axs - z) * ei)); v[1] = fmax(v[1], fabs(z * ei)); v[2] = fmax(v[2], fabs(axs * ei));
         u[0] = fmax(u[0], fabs(axs - z)); u[1] = fmax(u[1], fabs(z)); u[2] = fmax(u[2], fabs(axs));
         // slack variable: q^ + A'y (its P block is zero)
-        const double di = 1.0 / w.Ds[si];
-        const double qs = c * a.pi * w.Ds[si];
-        const double aty = a.kd * w.sl[si] * w.yp[i] + w.bs[si] * w.ys[si];
+        const double di = 1.0 / W_Ds[si];
+        const double qs = c * a.pi * W_Ds[si];
+        const double aty = a.kd * W_sl[si] * W_yp[i] + W_bs[si] * W_ys[si];
         v[3] = fmax(v[3], fabs((qs + aty) * di)); v[4] = fmax(v[4], fabs(qs * di)); v[5] = fmax(v[5], fabs(aty * di));
         u[3] = fmax(u[3], fabs(qs + aty)); u[4] = fmax(u[4], fabs(qs)); u[5] = fmax(u[5], fabs(aty));
       }
     }
-    for (int i = tid; i < m_nl; i += TEAM) w.wp[i] = a.kd * w.yp[i];
-    for (int j = tid; j < n; j += TEAM) w.xt[j] = w.D[j] * w.x[j];
+    for (int i = tid; i < m_nl; i += TEAM) W_wp[i] = a.kd * W_yp[i];
+    for (int j = tid; j < n; j += TEAM) W_xt[j] = W_D[j] * W_x[j];
     sync();
     for (int j = tid; j < n; j += TEAM) {
-      const double ax = w.bx[j] * w.x[j], ei = 1.0 / w.Eb[j], z = w.zb[j];
+      const double ax = W_bx[j] * W_x[j], ei = 1.0 / W_Eb[j], z = W_zb[j];
       v[0] = fmax(v[0], fabs((ax - z) * ei)); v[1] = fmax(v[1], fabs(z * ei)); v[2] = fmax(v[2], fabs(ax * ei));
       u[0] = fmax(u[0], fabs(ax - z)); u[1] = fmax(u[1], fabs(z)); u[2] = fmax(u[2], fabs(ax));
       double px = 0.0;
-      if (a.closest) px = 2.0 * w.xt[j];
+      if (a.closest) px = 2.0 * W_xt[j];
       else if (Qg || a.has_hq)
-        for (int k = 0; k < n; k++) px += psym(k, j) * w.xt[k];
-      px *= c * w.D[j];
-      const double aty = gatherAT(j, w.yl, w.wp) + w.bx[j] * w.yb[j];
-      const double di = 1.0 / w.D[j], q = w.qh[j];
+        for (int k = 0; k < n; k++) px += psym(k, j) * W_xt[k];
+      px *= c * W_D[j];
+      const double aty = gatherAT(j, W_yl, W_wp) + W_bx[j] * W_yb[j];
+      const double di = 1.0 / W_D[j], q = W_qh[j];
       v[3] = fmax(v[3], fabs((q + px + aty) * di)); v[4] = fmax(v[4], fabs(q * di));
       v[5] = fmax(v[5], fabs(aty * di)); v[6] = fmax(v[6], fabs(px * di));
       u[3] = fmax(u[3], fabs(q + px + aty)); u[4] = fmax(u[4], fabs(q)); u[5] = fmax(u[5], fabs(aty));
       u[6] = fmax(u[6], fabs(px));
     }
-    Team<TEAM>::reduce_max(v, w.red);
+    Team<TEAM>::reduce_max(v, W_red);
     if (sc) {
-      Team<TEAM>::reduce_max(u, w.red);
+      Team<TEAM>::reduce_max(u, W_red);
       for (int k = 0; k < 7; k++) sc[k] = u[k];
     }
     const double pri_res = v[0], dua_res = cinv * v[3];
@@ -434,49 +447,49 @@ struct QPSolver {
     SCO_QP_LOCALS
     double nv[1] = {0.0}, lhs[1] = {0.0};
     for (int r = tid; r < m_lin; r += TEAM) {
-      const double dy = proj_dy(w.dyl[r], w.ll[r], w.ul[r]);
-      w.dyl[r] = dy;
-      nv[0] = fmax(nv[0], fabs(w.El[r] * dy));
-      lhs[0] += w.ul[r] * fmax(dy, 0.0) + w.ll[r] * fmin(dy, 0.0);
+      const double dy = proj_dy(W_dyl[r], W_ll[r], W_ul[r]);
+      W_dyl[r] = dy;
+      nv[0] = fmax(nv[0], fabs(W_El[r] * dy));
+      lhs[0] += W_ul[r] * fmax(dy, 0.0) + W_ll[r] * fmin(dy, 0.0);
     }
     for (int i = tid; i < m_nl; i += TEAM) {
-      const double dy = proj_dy(w.dyp[i], w.lp[i], w.up[i]);
-      w.dyp[i] = dy;
-      w.wp[i] = a.kd * dy;
-      nv[0] = fmax(nv[0], fabs(w.Ep[i] * dy));
-      lhs[0] += a.kd * (w.up[i] * fmax(dy, 0.0) + w.lp[i] * fmin(dy, 0.0));
-      for (int k2 = 0; k2 <= S.row_eq[i]; k2++) {
+      const double dy = proj_dy(W_dyp[i], W_lp[i], W_up[i]);
+      W_dyp[i] = dy;
+      W_wp[i] = a.kd * dy;
+      nv[0] = fmax(nv[0], fabs(W_Ep[i] * dy));
+      lhs[0] += a.kd * (W_up[i] * fmax(dy, 0.0) + W_lp[i] * fmin(dy, 0.0));
+      for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) {
         const int si = k2 * ms + i;
-        const double us = OSQP_INFTY * w.Es[si];
-        const double dys = proj_dy(w.dys[si], 0.0, us);
-        w.dys[si] = dys;
-        nv[0] = fmax(nv[0], fabs(w.Es[si] * dys));
+        const double us = OSQP_INFTY * W_Es[si];
+        const double dys = proj_dy(W_dys[si], 0.0, us);
+        W_dys[si] = dys;
+        nv[0] = fmax(nv[0], fabs(W_Es[si] * dys));
         lhs[0] += us * fmax(dys, 0.0);
       }
     }
     for (int j = tid; j < n; j += TEAM) {
-      const double dy = proj_dy(w.dyb[j], w.lb[j], w.ub[j]);
-      w.dyb[j] = dy;
-      nv[0] = fmax(nv[0], fabs(w.Eb[j] * dy));
-      lhs[0] += w.ub[j] * fmax(dy, 0.0) + w.lb[j] * fmin(dy, 0.0);
+      const double dy = proj_dy(W_dyb[j], W_lb[j], W_ub[j]);
+      W_dyb[j] = dy;
+      nv[0] = fmax(nv[0], fabs(W_Eb[j] * dy));
+      lhs[0] += W_ub[j] * fmax(dy, 0.0) + W_lb[j] * fmin(dy, 0.0);
     }
-    Team<TEAM>::reduce_max(nv, w.red);
-    Team<TEAM>::reduce_sum(lhs, w.red);
+    Team<TEAM>::reduce_max(nv, W_red);
+    Team<TEAM>::reduce_sum(lhs, W_red);
     sync();
     bool res = false;
     if (nv[0] > eps && lhs[0] < -eps * nv[0]) {
       double mv[1] = {0.0};
       for (int j = tid; j < n; j += TEAM) {
-        const double aty = gatherAT(j, w.dyl, w.wp) + w.bx[j] * w.dyb[j];
-        mv[0] = fmax(mv[0], fabs(aty / w.D[j]));
+        const double aty = gatherAT(j, W_dyl, W_wp) + W_bx[j] * W_dyb[j];
+        mv[0] = fmax(mv[0], fabs(aty / W_D[j]));
       }
       for (int i = tid; i < m_nl; i += TEAM)
-        for (int k2 = 0; k2 <= S.row_eq[i]; k2++) {
+        for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) {
           const int si = k2 * ms + i;
-          const double aty = w.sl[si] * w.wp[i] + w.bs[si] * w.dys[si];
-          mv[0] = fmax(mv[0], fabs(aty / w.Ds[si]));
+          const double aty = W_sl[si] * W_wp[i] + W_bs[si] * W_dys[si];
+          mv[0] = fmax(mv[0], fabs(aty / W_Ds[si]));
         }
-      Team<TEAM>::reduce_max(mv, w.red);
+      Team<TEAM>::reduce_max(mv, W_red);
       res = mv[0] < eps * nv[0];
     }
     sync();
@@ -488,18 +501,18 @@ struct QPSolver {
     SCO_QP_LOCALS
     double nv[1] = {0.0}, qd[1] = {0.0};
     for (int j = tid; j < n; j += TEAM) {
-      nv[0] = fmax(nv[0], fabs(w.D[j] * w.dxv[j]));
-      qd[0] += w.qh[j] * w.dxv[j];
-      w.xt[j] = w.D[j] * w.dxv[j];
+      nv[0] = fmax(nv[0], fabs(W_D[j] * W_dxv[j]));
+      qd[0] += W_qh[j] * W_dxv[j];
+      W_xt[j] = W_D[j] * W_dxv[j];
     }
     for (int i = tid; i < m_nl; i += TEAM)
-      for (int k2 = 0; k2 <= S.row_eq[i]; k2++) {
+      for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) {
         const int si = k2 * ms + i;
-        nv[0] = fmax(nv[0], fabs(w.Ds[si] * w.dss[si]));
-        qd[0] += c * a.pi * w.Ds[si] * w.dss[si];
+        nv[0] = fmax(nv[0], fabs(W_Ds[si] * W_dss[si]));
+        qd[0] += c * a.pi * W_Ds[si] * W_dss[si];
       }
-    Team<TEAM>::reduce_max(nv, w.red);
-    Team<TEAM>::reduce_sum(qd, w.red);
+    Team<TEAM>::reduce_max(nv, W_red);
+    Team<TEAM>::reduce_sum(qd, W_red);
     sync();
     bool res = false;
     const double thr = c * eps * nv[0];
@@ -507,39 +520,39 @@ struct QPSolver {
       double pv[1] = {0.0};
       for (int j = tid; j < n; j += TEAM) {
         double px = 0.0;
-        if (a.closest) px = 2.0 * w.xt[j];
+        if (a.closest) px = 2.0 * W_xt[j];
         else if (Qg || a.has_hq)
-          for (int k = 0; k < n; k++) px += psym(k, j) * w.xt[k];
+          for (int k = 0; k < n; k++) px += psym(k, j) * W_xt[k];
         pv[0] = fmax(pv[0], fabs(c * px));  // Dinv .* (c D Psym D dx) = c * Psym (D dx)
       }
-      Team<TEAM>::reduce_max(pv, w.red);
+      Team<TEAM>::reduce_max(pv, W_red);
       if (pv[0] < thr) {
         const double lim = eps * nv[0];
         double bad[1] = {0.0};
         for (int r = tid; r < m_lin; r += TEAM) {
-          const double adx = lin_row_dot(r, w.dxv) / w.El[r];
-          if ((w.ul[r] < OSQP_INFTY * OSQP_MIN_SCALING && adx > lim) ||
-              (w.ll[r] > -OSQP_INFTY * OSQP_MIN_SCALING && adx < -lim)) bad[0] = 1.0;
+          const double adx = lin_row_dot(r, W_dxv) / W_El[r];
+          if ((W_ul[r] < OSQP_INFTY * OSQP_MIN_SCALING && adx > lim) ||
+              (W_ll[r] > -OSQP_INFTY * OSQP_MIN_SCALING && adx < -lim)) bad[0] = 1.0;
         }
         for (int i = tid; i < m_nl; i += TEAM) {
-          double adx = pen_row_dot(i, w.dxv) + w.sl[i] * w.dss[i];
-          if (S.row_eq[i]) adx += w.sl[ms + i] * w.dss[ms + i];
-          adx /= w.Ep[i];
-          if ((w.up[i] < OSQP_INFTY * OSQP_MIN_SCALING && adx > lim) ||
-              (w.lp[i] > -OSQP_INFTY * OSQP_MIN_SCALING && adx < -lim)) bad[0] = 1.0;
-          for (int k2 = 0; k2 <= S.row_eq[i]; k2++) {
+          double adx = pen_row_dot(i, W_dxv) + W_sl[i] * W_dss[i];
+          if (__ldg(S.row_eq + (i))) adx += W_sl[ms + i] * W_dss[ms + i];
+          adx /= W_Ep[i];
+          if ((W_up[i] < OSQP_INFTY * OSQP_MIN_SCALING && adx > lim) ||
+              (W_lp[i] > -OSQP_INFTY * OSQP_MIN_SCALING && adx < -lim)) bad[0] = 1.0;
+          for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) {
             const int si = k2 * ms + i;
-            const double ads = w.bs[si] * w.dss[si] / w.Es[si];
-            if ((OSQP_INFTY * w.Es[si] < OSQP_INFTY * OSQP_MIN_SCALING && ads > lim) || ads < -lim)
+            const double ads = W_bs[si] * W_dss[si] / W_Es[si];
+            if ((OSQP_INFTY * W_Es[si] < OSQP_INFTY * OSQP_MIN_SCALING && ads > lim) || ads < -lim)
               bad[0] = 1.0;
           }
         }
         for (int j = tid; j < n; j += TEAM) {
-          const double adx = w.bx[j] * w.dxv[j] / w.Eb[j];
-          if ((w.ub[j] < OSQP_INFTY * OSQP_MIN_SCALING && adx > lim) ||
-              (w.lb[j] > -OSQP_INFTY * OSQP_MIN_SCALING && adx < -lim)) bad[0] = 1.0;
+          const double adx = W_bx[j] * W_dxv[j] / W_Eb[j];
+          if ((W_ub[j] < OSQP_INFTY * OSQP_MIN_SCALING && adx > lim) ||
+              (W_lb[j] > -OSQP_INFTY * OSQP_MIN_SCALING && adx < -lim)) bad[0] = 1.0;
         }
-        Team<TEAM>::reduce_max(bad, w.red);
+        Team<TEAM>::reduce_max(bad, W_red);
         res = bad[0] == 0.0;
       }
     }
@@ -548,18 +561,18 @@ struct QPSolver {
   }
 
   // ================================================================== the ADMM loop
-  // On return w.x (user variables) and w.s (slacks) hold the UNSCALED solution.
+  // On return W_x (user variables) and W_s (slacks) hold the UNSCALED solution.
   // generic shared-memory ADMM loop; returns the status (0 = max_iter reached without a verdict)
   __device__ __noinline__ int generic_loop(int &iter_out, bool &checked_out, QPResult &res) {
     SCO_QP_LOCALS
     const double sigma = st.sigma, alpha = st.alpha, oma = 1.0 - st.alpha;
-    for (int j = tid; j < n; j += TEAM) { w.x[j] = 0.0; w.zb[j] = 0.0; w.yb[j] = 0.0; }
-    for (int r = tid; r < m_lin; r += TEAM) { w.zl[r] = 0.0; w.yl[r] = 0.0; }
+    for (int j = tid; j < n; j += TEAM) { W_x[j] = 0.0; W_zb[j] = 0.0; W_yb[j] = 0.0; }
+    for (int r = tid; r < m_lin; r += TEAM) { W_zl[r] = 0.0; W_yl[r] = 0.0; }
     for (int i = tid; i < m_nl; i += TEAM) {
-      w.zp[i] = 0.0; w.yp[i] = 0.0;
-      for (int k2 = 0; k2 <= S.row_eq[i]; k2++) {
+      W_zp[i] = 0.0; W_yp[i] = 0.0;
+      for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) {
         const int si = k2 * ms + i;
-        w.s[si] = 0.0; w.zs[si] = 0.0; w.ys[si] = 0.0;
+        W_s[si] = 0.0; W_zs[si] = 0.0; W_ys[si] = 0.0;
       }
     }
     sync();
@@ -572,92 +585,110 @@ struct QPSolver {
       const bool can_check = st.check_termination && (iter % st.check_termination == 0);
       const bool do_rho = st.adaptive_rho && interval && (iter % interval == 0);
       const bool want_delta = can_check || do_rho;
+#ifdef SCO_TIMING
+      long long tph = clock64();
+#define SCO_PH(k) { sync(); const long long tq_ = clock64(); res.cyc_c[k] += tq_ - tph; tph = tq_; }
+#else
+#define SCO_PH(k)
+#endif
       // ---- P1: row weights  w = rho z - y, slack elimination
-      for (int r = tid; r < m_lin; r += TEAM) w.wl[r] = w.rl[r] * w.zl[r] - w.yl[r];
+      for (int r = tid; r < m_lin; r += TEAM) W_wl[r] = W_rl[r] * W_zl[r] - W_yl[r];
       for (int i = tid; i < m_nl; i += TEAM) {
-        const double wpen = w.rp[i] * w.zp[i] - w.yp[i];
-        const double kr = a.kd * w.rp[i];
-        const double r1 = sigma * w.s[i] - cpi * w.Ds[i] + a.kd * w.sl[i] * wpen +
-                          w.bs[i] * (w.rs[i] * w.zs[i] - w.ys[i]);
-        if (S.row_eq[i]) {
+        const double wpen = W_rp[i] * W_zp[i] - W_yp[i];
+        const double kr = a.kd * W_rp[i];
+        const double r1 = sigma * W_s[i] - cpi * W_Ds[i] + a.kd * W_sl[i] * wpen +
+                          W_bs[i] * (W_rs[i] * W_zs[i] - W_ys[i]);
+        if (__ldg(S.row_eq + (i))) {
           const int i2 = ms + i;
-          const double r2 = sigma * w.s[i2] - cpi * w.Ds[i2] + a.kd * w.sl[i2] * wpen +
-                            w.bs[i2] * (w.rs[i2] * w.zs[i2] - w.ys[i2]);
-          const double g1 = w.Minv[3 * i] * r1 + w.Minv[3 * i + 1] * r2;
-          const double g2 = w.Minv[3 * i + 1] * r1 + w.Minv[3 * i + 2] * r2;
-          w.gs[i] = g1; w.gs[i2] = g2;
-          w.wp[i] = a.kd * wpen - kr * (w.sl[i] * g1 + w.sl[i2] * g2);
+          const double r2 = sigma * W_s[i2] - cpi * W_Ds[i2] + a.kd * W_sl[i2] * wpen +
+                            W_bs[i2] * (W_rs[i2] * W_zs[i2] - W_ys[i2]);
+          const double g1 = W_Minv[3 * i] * r1 + W_Minv[3 * i + 1] * r2;
+          const double g2 = W_Minv[3 * i + 1] * r1 + W_Minv[3 * i + 2] * r2;
+          W_gs[i] = g1; W_gs[i2] = g2;
+          W_wp[i] = a.kd * wpen - kr * (W_sl[i] * g1 + W_sl[i2] * g2);
         } else {
-          const double g1 = w.Minv[3 * i] * r1;
-          w.gs[i] = g1;
-          w.wp[i] = a.kd * wpen - kr * w.sl[i] * g1;
+          const double g1 = W_Minv[3 * i] * r1;
+          W_gs[i] = g1;
+          W_wp[i] = a.kd * wpen - kr * W_sl[i] * g1;
         }
       }
       sync();
+      SCO_PH(0)
       // ---- P2: reduced right-hand side
       for (int j = tid; j < n; j += TEAM)
-        w.xt[j] = sigma * w.x[j] - w.qh[j] + w.bx[j] * (w.rb[j] * w.zb[j] - w.yb[j]) +
-                  gatherAT(j, w.wl, w.wp);
+        W_xt[j] = sigma * W_x[j] - W_qh[j] + W_bx[j] * (W_rb[j] * W_zb[j] - W_yb[j]) +
+                  gatherAT(j, W_wl, W_wp);
       sync();
+      SCO_PH(1)
       // ---- P3: x~ = S^-1 rhs ; x, bound rows
       for (int j = tid; j < n; j += TEAM) {
-        double acc0 = 0.0, acc1 = 0.0;
+        // four independent chains, loads issued ahead of the FMAs (a two-chain loop waited for every
+        // shared-memory round trip: 28 cycles per term)
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
         int k = 0;
-        for (; k + 1 < n; k += 2) {
-          acc0 += w.Sm[k * n + j] * w.xt[k];
-          acc1 += w.Sm[(k + 1) * n + j] * w.xt[k + 1];
+#pragma unroll 2
+        for (; k + 3 < n; k += 4) {
+          const double s0 = W_Sm[k * n + j], s1 = W_Sm[(k + 1) * n + j], s2 = W_Sm[(k + 2) * n + j], s3 = W_Sm[(k + 3) * n + j];
+          acc0 = fma(s0, W_xt[k], acc0);
+          acc1 = fma(s1, W_xt[k + 1], acc1);
+          acc2 = fma(s2, W_xt[k + 2], acc2);
+          acc3 = fma(s3, W_xt[k + 3], acc3);
         }
-        if (k < n) acc0 += w.Sm[k * n + j] * w.xt[k];
+        for (; k < n; k++) acc0 = fma(W_Sm[k * n + j], W_xt[k], acc0);
+        acc0 += acc2;
+        acc1 += acc3;
         const double xtil = acc0 + acc1;
-        w.xt2[j] = xtil;
-        const double xo = w.x[j];
+        W_xt2[j] = xtil;
+        const double xo = W_x[j];
         const double xn = alpha * xtil + oma * xo;
-        w.x[j] = xn;
-        const double zt = w.bx[j] * xtil;
-        const double vv = alpha * zt + oma * w.zb[j];
-        const double zn = clampd(vv + w.yb[j] / w.rb[j], w.lb[j], w.ub[j]);
-        const double dy = w.rb[j] * (vv - zn);
-        w.yb[j] += dy;
-        w.zb[j] = zn;
-        if (want_delta) { w.dxv[j] = xn - xo; w.dyb[j] = dy; }
+        W_x[j] = xn;
+        const double zt = W_bx[j] * xtil;
+        const double vv = alpha * zt + oma * W_zb[j];
+        const double zn = clampd(vv + W_yb[j] / W_rb[j], W_lb[j], W_ub[j]);
+        const double dy = W_rb[j] * (vv - zn);
+        W_yb[j] += dy;
+        W_zb[j] = zn;
+        if (want_delta) { W_dxv[j] = xn - xo; W_dyb[j] = dy; }
       }
       sync();
+      SCO_PH(2)
       // ---- P4: rows
       for (int r = tid; r < m_lin; r += TEAM) {
-        const double zt = lin_row_dot(r, w.xt2);
-        const double vv = alpha * zt + oma * w.zl[r];
-        const double zn = clampd(vv + w.yl[r] / w.rl[r], w.ll[r], w.ul[r]);
-        const double dy = w.rl[r] * (vv - zn);
-        w.yl[r] += dy;
-        w.zl[r] = zn;
-        if (want_delta) w.dyl[r] = dy;
+        const double zt = lin_row_dot(r, W_xt2);
+        const double vv = alpha * zt + oma * W_zl[r];
+        const double zn = clampd(vv + W_yl[r] / W_rl[r], W_ll[r], W_ul[r]);
+        const double dy = W_rl[r] * (vv - zn);
+        W_yl[r] += dy;
+        W_zl[r] = zn;
+        if (want_delta) W_dyl[r] = dy;
       }
       for (int i = tid; i < m_nl; i += TEAM) {
-        const double t = pen_row_dot(i, w.xt2);
-        const int eq = S.row_eq[i];
+        const double t = pen_row_dot(i, W_xt2);
+        const int eq = __ldg(S.row_eq + (i));
         double zt = t;
         for (int k2 = 0; k2 <= eq; k2++) {
           const int si = k2 * ms + i;
-          const double stil = w.gs[si] - w.hs[si] * t;
-          zt += w.sl[si] * stil;
-          const double so = w.s[si];
+          const double stil = W_gs[si] - W_hs[si] * t;
+          zt += W_sl[si] * stil;
+          const double so = W_s[si];
           const double sn = alpha * stil + oma * so;
-          w.s[si] = sn;
-          const double zts = w.bs[si] * stil;
-          const double vs = alpha * zts + oma * w.zs[si];
-          const double zns = clampd(vs + w.ys[si] / w.rs[si], 0.0, OSQP_INFTY * w.Es[si]);
-          const double dys = w.rs[si] * (vs - zns);
-          w.ys[si] += dys;
-          w.zs[si] = zns;
-          if (want_delta) { w.dss[si] = sn - so; w.dys[si] = dys; }
+          W_s[si] = sn;
+          const double zts = W_bs[si] * stil;
+          const double vs = alpha * zts + oma * W_zs[si];
+          const double zns = clampd(vs + W_ys[si] / W_rs[si], 0.0, OSQP_INFTY * W_Es[si]);
+          const double dys = W_rs[si] * (vs - zns);
+          W_ys[si] += dys;
+          W_zs[si] = zns;
+          if (want_delta) { W_dss[si] = sn - so; W_dys[si] = dys; }
         }
-        const double vv = alpha * zt + oma * w.zp[i];
-        const double zn = clampd(vv + w.yp[i] / w.rp[i], w.lp[i], w.up[i]);
-        const double dy = w.rp[i] * (vv - zn);
-        w.yp[i] += dy;
-        w.zp[i] = zn;
-        if (want_delta) w.dyp[i] = dy;
+        const double vv = alpha * zt + oma * W_zp[i];
+        const double zn = clampd(vv + W_yp[i] / W_rp[i], W_lp[i], W_up[i]);
+        const double dy = W_rp[i] * (vv - zn);
+        W_yp[i] += dy;
+        W_zp[i] = zn;
+        if (want_delta) W_dyp[i] = dy;
       }
+      SCO_PH(3)
       checked = false;
       if (want_delta) {
         sync();
@@ -680,6 +711,7 @@ struct QPSolver {
         }
         sync();
       }
+      SCO_PH(4)
     }
     iter_out = iter;
     checked_out = checked;
@@ -734,7 +766,7 @@ struct QPSolver {
     // unscale
     for (int j = tid; j < n; j += TEAM) w.x[j] *= w.D[j];
     for (int i = tid; i < m_nl; i += TEAM)
-      for (int k2 = 0; k2 <= S.row_eq[i]; k2++) w.s[k2 * ms + i] *= w.Ds[k2 * ms + i];
+      for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) w.s[k2 * ms + i] *= w.Ds[k2 * ms + i];
     sync();
     res.status = status;
     res.iters = iter;

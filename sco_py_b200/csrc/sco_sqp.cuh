@@ -166,12 +166,12 @@ struct SqpSolver {
     double v[1 + SCO_DEV_MAX_GROUPS];
     for (int k = 0; k < 1 + SCO_DEV_MAX_GROUPS; k++) v[k] = 0.0;
     for (int i = tid; i < m_nl; i += TEAM) {
-      const int go = S.row_goff[i], wd = S.row_w[i];
+      const int go = __ldg(S.row_goff + (i)), wd = __ldg(S.row_w + (i));
       double acc = w.bb[i];
-      for (int k = 0; k < wd; k++) acc += Jg[go + k] * xc[S.jcol_g[go + k]];
-      const double pen = S.row_eq[i] ? fabs(acc) : fmax(acc, 0.0);
+      for (int k = 0; k < wd; k++) acc += Jg[go + k] * xc[__ldg(S.jcol_g + (go + k))];
+      const double pen = __ldg(S.row_eq + (i)) ? fabs(acc) : fmax(acc, 0.0);
       v[0] += pen;
-      const int gm = S.row_gmask[i];
+      const int gm = __ldg(S.row_gmask + (i));
       for (int g = 0; g < ng; g++)
         if ((gm >> g) & 1) v[1 + g] += pen;
     }
@@ -189,12 +189,12 @@ struct SqpSolver {
       const DevBlock &B = S.blocks[bi];
       const double *val = field_ptr(S, B.val, prm);
       for (int r = tid; r < B.m; r += TEAM) {
-        const int i = B.row0 + r, go = S.row_goff[i], wd = S.row_w[i];
+        const int i = B.row0 + r, go = __ldg(S.row_goff + (i)), wd = __ldg(S.row_w + (i));
         double acc = 0.0;
         uint32_t mk = 0;
         for (int k = 0; k < wd; k++) {
           const double jv = Jg[go + k];
-          acc += jv * xc[S.jcol_g[go + k]];
+          acc += jv * xc[__ldg(S.jcol_g + (go + k))];
           if (jv != 0.0) mk |= (1u << k);
         }
         w.bb[i] = -acc + w.fv[i] - (val ? val[r] : 0.0);
