@@ -7,7 +7,7 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libsco_b200.so")
+LIB_PATH = os.environ.get("SCO_B200_LIB", os.path.join(PKG, "libsco_b200.so"))  # override: A/B runs of two builds
 
 MAX_BLOCKS = 8
 MAX_GROUPS = 8
