@@ -305,14 +305,14 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   S.dense_kind = 0;
   if (desc->m_lin == 0 && S.obj_len == 0 && desc->n_blocks == 1 && desc->blocks[0].family == SCO_FAM_QUADFORM &&
       desc->blocks[0].cnt_type == SCO_CNT_LEQ) {
-    static const int table[][2] = {{8, 6}, {12, 16}, {20, 30}, {32, 32}};  // keep in sync with sco_qp_dense.cuh
+    static const int table[][2] = {{8, 6}, {12, 16}, {20, 30}, {32, 32}};  // keep in sync with QPSolver::solve in sco_qp.cuh
     for (int k = 0; k < 4; k++)
       if (n <= table[k][0] && m_nl <= table[k][1]) { S.dense_kind = k + 1; break; }
   }
   // ---- team size and shared-memory layout
   const int work = std::max(std::max(n, m_nl), desc->m_lin);
   int team = work <= 40 ? 32 : work <= 96 ? 64 : work <= 192 ? 128 : 256;
-  if (S.dense_kind) team = 64;  // two warps per problem: rows | variables (sco_qp_dense.inl)
+  if (S.dense_kind) team = 64;  // two warps per problem: rows | variables (sco_dense.cuh)
   for (;;) {
     build_layout(S, team);
     h->smem_bytes = (size_t)(S.L.total + ((n + 1) & ~1)) * sizeof(double);

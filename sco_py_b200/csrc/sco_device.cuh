@@ -2,8 +2,9 @@
 //
 // One thread TEAM (a warp, or a CTA of 2..8 warps) owns one problem at a time and keeps the
 // whole working set of its current penalty QP in shared memory for the duration of the ADMM
-// solve ("resident regime").  All sizes are run-time values taken from
-// the structure; the shared-memory carve-up (Layout) is computed once on the host.
+// solve ("resident regime").  For generic structures all sizes are run-time
+// values and the shared-memory carve-up (Layout) is computed once on the host; dense hinge-only
+// structures use the compile-time layout DenseL below (sco_dense.cuh).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -52,7 +52,7 @@ const TeamOps *sco_team_ops_32();
 const TeamOps *sco_team_ops_64();
 const TeamOps *sco_team_ops_128();
 const TeamOps *sco_team_ops_256();
-// dense kinds (two-warp register-resident ADMM loop, sco_qp_dense.inl); convexify / merit are null
+// dense kinds (two-warp register-resident ADMM loop, sco_dense.cuh); convexify / merit are null
 const TeamOps *sco_dense_ops_1();
 const TeamOps *sco_dense_ops_2();
 const TeamOps *sco_dense_ops_3();

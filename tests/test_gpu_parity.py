@@ -180,7 +180,7 @@ def test_batch_properties_at_scale(engines):
 
 
 def test_dense_register_path_matches_generic_path(engines):
-    """The two-warp register-resident ADMM loop (sco_qp_dense.inl) against the generic shared-memory
+    """The two-warp register-resident ADMM loop (sco_dense.cuh) against the generic shared-memory
     loop on the same QPs: same status, same iteration count, x to 1e-9; and the same SQP outcome."""
     from sco_py_b200.engine import make_settings
     eng, st, params, x0 = engines["qcqp"]
