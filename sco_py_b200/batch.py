@@ -137,10 +137,17 @@ def _csr(A):
     return np.asarray(rowptr, np.int32), np.asarray(col, np.int32), np.asarray(val, np.float64)
 
 
-def compile_batch(probs):
+def group_key(cp):
+    """What two compiled problems must have in common to go into one launch."""
+    return (cp.x0.size, None if cp.lin_A is None else (cp.lin_A.shape, cp.lin_A.tobytes()), tuple(cp.gids),
+            tuple((b[0].family, b[0].m, b[1], tuple(b[0].ipar), tuple(b[3])) for b in cp.blocks),
+            None if cp.obj_prog is None else cp.obj_prog.n_instr)
+
+
+def compile_batch(probs, compiled=None):
     """-> (Structure, params[B, stride], x0[B, n], compiled list).  All problems must share the
     structure: variable count, linear-row coefficients, constraint block families / sizes / groups."""
-    cps = [compile_problem(p) for p in probs]
+    cps = compiled if compiled is not None else [compile_problem(p) for p in probs]
     c0 = cps[0]
     n = c0.x0.size
     B = len(cps)
@@ -216,7 +223,7 @@ def compile_batch(probs):
         blocks.append(Block(fam.family, ctype, fam.m, pf, vf, ipar=list(fam.ipar), group_mask=mask or 1, jw=fam.jw))
     ng = max(1, len(c0.gids))
     overlap = np.zeros((ng, ng), dtype=np.int32)
-    ov = getattr(probs[0], "_cnt_groups_overlap", {})
+    ov = getattr(probs[0], "_cnt_groups_overlap", {}) if probs else {}
     for g, others in ov.items():
         for o in others:
             if g in c0.gids and o in c0.gids:

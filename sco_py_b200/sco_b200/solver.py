@@ -50,20 +50,31 @@ class Solver(object):
         if method != "penalty_sqp":
             raise Exception("This method is not supported.")
         from ..engine import Engine, make_settings
-        st, params, x0, cps = batch.compile_batch(probs)
-        key = (batch.signature(st), device)
-        if key not in self._engines:
-            self._engines[key] = Engine(st, device=device)
-        eng = self._engines[key]
         settings = make_settings(
             solver={k: getattr(self, k) for k in self._ATTRS},
             osqp=dict(eps_abs=osqp_eps_abs, eps_rel=osqp_eps_rel, max_iter=osqp_max_iter, rho=rho,
                       adaptive_rho=adaptive_rho, sigma=sigma))
-        out = eng.solve_batch_host(params, x0, settings)
-        for i, cp in enumerate(cps):
-            batch.scatter_solution(cp, out["x"][i])
-            probs[i].nonconverged_groups = []
-            probs[i]._stage = None
+        # problems of different structures are bucketed: one launch per structure (BASELINE.json configs[4])
+        compiled = [batch.compile_problem(p) for p in probs]
+        buckets = {}
+        for i, cp in enumerate(compiled):
+            buckets.setdefault(batch.group_key(cp), []).append(i)
+        B = len(probs)
+        out = dict(x=[None] * B, verdict=np.zeros(B, np.int32), merit=np.zeros(B), objective=np.zeros(B),
+                   max_vio=np.zeros(B), stats=np.zeros((B, 4), np.int32))
+        for idx in buckets.values():
+            st, params, x0, cps = batch.compile_batch([probs[i] for i in idx], compiled=[compiled[i] for i in idx])
+            key = (batch.signature(st), device)
+            if key not in self._engines:
+                self._engines[key] = Engine(st, device=device)
+            res = self._engines[key].solve_batch_host(params, x0, settings)
+            for k, i in enumerate(idx):
+                batch.scatter_solution(cps[k], res["x"][k])
+                probs[i].nonconverged_groups = []
+                probs[i]._stage = None
+                out["x"][i] = res["x"][k]
+                for name in ("verdict", "merit", "objective", "max_vio", "stats"):
+                    out[name][i] = res[name][k]
         self.last_report = out
         if verbose:
             print("sco_b200: %d problems, %d converged, mean ADMM iterations %.0f"

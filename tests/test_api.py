@@ -243,3 +243,18 @@ def test_edge_cases_empty_batch_qp_only_problem_and_size_limits():
         assert (int(out["verdict"][i]) == 1) == ref["success"]
         assert np.abs(out["x"][i].cpu().numpy() - ref["x"]).max() <= 1e-4 * max(1.0, np.abs(ref["x"]).max())
     eng.close()
+
+
+@pytest.mark.gpu
+def test_solve_batch_buckets_mixed_structures():
+    """Solver.solve_batch on problems of different structures: one launch per structure, results in
+    the caller's order."""
+    built, refs = [], []
+    for n, m, first in ((8, 6, 0), (12, 10, 0), (8, 6, 1), (12, 10, 1), (8, 6, 2)):
+        st, params, x0 = W.gen_qcqp(1, n=n, m=m, first=first)
+        built.append(api_builder.build_prob(st, params[0], x0[0]))
+        refs.append(sqp_port.solve(st, params[0], x0[0], solver=W.SOLVER_SETTINGS))
+    ok = _solver().solve_batch([p for p, _ in built], method="penalty_sqp")
+    for (prob, var), ref, o in zip(built, refs, ok):
+        assert o == ref["success"]
+        assert np.abs(var.get_value()[:, 0] - ref["x"]).max() <= 1e-4 * max(1.0, np.abs(ref["x"]).max())
