@@ -127,6 +127,7 @@ def workload_config(args, per_gpu_batch):
     return {"workload": names[args.config], "batch_per_gpu": per_gpu_batch,
             "global_batch": per_gpu_batch * args.gpus, "parallelism": "problems sharded, dp%d" % args.gpus,
             "pipelining": "steps (independent batches) round-robin over %d CUDA streams" % max(1, min(getattr(args, "streams", 1), 4)),
+            "queue_order": getattr(args, "order", "index"),
             "solver": "penalty_sqp, test_solver.py:15-25 hyper-parameters (mu0=1), OSQP eps_abs 1e-6 eps_rel 1e-9 "
                       "rho 0.1 fixed, reference quirks C-1..C-3 on",
             "l2": "inputs (%.2f GB of parameters per GPU) exceed the 126 MB L2; no flush needed"
@@ -276,17 +277,23 @@ def run_b200_arm(args):
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
     cur = torch.cuda.current_stream(dev)
 
+    order = [None]  # --order profile: longest problems first, from the statistics of a previous solve
+
     def run_steps(count):
         outs = []
         for s_ in streams:
             s_.wait_stream(cur)
         for i in range(count):
-            outs.append(eng.solve_batch(d_params, d_x0, settings, stream=streams[i % n_streams]))
+            outs.append(eng.solve_batch(d_params, d_x0, settings, stream=streams[i % n_streams], order=order[0]))
         for s_ in streams:
             cur.wait_stream(s_)
         return outs
 
-    run_steps(args.warmup)
+    warm = run_steps(args.warmup)
+    if args.order == "profile" and warm:
+        torch.cuda.synchronize()
+        order[0] = torch.argsort(warm[-1]["stats"][:, 2], descending=True).to(torch.int32)
+        run_steps(1)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -447,6 +454,9 @@ def main():
     ap.add_argument("--config", default="qcqp", choices=["qcqp", "point_robot", "arm"])
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--order", default="index", choices=["index", "profile"],
+                    help="work-queue order: index (default) or profile = longest first by the ADMM iteration counts "
+                         "of the last warm-up step (sco_solve_batch_ordered; for callers that re-solve similar batches)")
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the steps are pipelined over (1..4)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU sample (default: two per core)")
     ap.add_argument("--cpu-cores", type=int, default=0)

@@ -166,6 +166,15 @@ int sco_solve_batch(sco_handle *h, int64_t B, const double *d_params, const doub
                     const sco_settings *s, double *d_x_out, int32_t *d_verdict, double *d_merit,
                     double *d_objective, double *d_max_vio, int32_t *d_stats, void *stream);
 
+/* Same, with a processing order: the work queue hands out problem d_order[0], d_order[1], ... (a permutation
+ * of 0..B-1 on the device; NULL = index order).  Results stay at their own index.  Iteration counts are
+ * heavy-tailed and a problem is sequential, so a launch ends when its longest problem does; a caller that
+ * re-solves similar batches (replanning, MPC) passes last time's stats[:, 2] sorted in descending order. */
+int sco_solve_batch_ordered(sco_handle *h, int64_t B, const double *d_params, const double *d_x0,
+                            const sco_settings *s, double *d_x_out, int32_t *d_verdict, double *d_merit,
+                            double *d_objective, double *d_max_vio, int32_t *d_stats, const int32_t *d_order,
+                            void *stream);
+
 /* Launches of one handle may be in flight on several streams at once (each owns one of four launch
  * slots: work-queue counter + Jacobian scratch); calls on one handle must come from one host thread. */
 

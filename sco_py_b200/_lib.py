@@ -50,7 +50,7 @@ class CSettings(ctypes.Structure):
 
 
 EXPORTS = ["sco_last_error", "sco_default_settings", "sco_create", "sco_destroy", "sco_query",
-           "sco_solve_batch", "sco_solve_batch_host", "sco_solve_batch_host_async", "sco_convexify", "sco_qp_solve", "sco_merit",
+           "sco_solve_batch", "sco_solve_batch_ordered", "sco_solve_batch_host", "sco_solve_batch_host_async", "sco_convexify", "sco_qp_solve", "sco_merit",
            "sco_probe_fp64"]
 
 _lib = None
@@ -75,6 +75,8 @@ def load():
     lib.sco_query.argtypes = [c_vp, ctypes.POINTER(c_i64)]
     lib.sco_solve_batch.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(CSettings), c_vp, c_vp,
                                     c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.sco_solve_batch_ordered.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(CSettings), c_vp, c_vp,
+                                            c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.sco_solve_batch_host.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(CSettings), c_vp,
                                          c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.sco_solve_batch_host_async.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(CSettings), c_vp,

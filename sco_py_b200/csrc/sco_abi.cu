@@ -379,6 +379,14 @@ extern "C" int sco_solve_batch(sco_handle *h, int64_t B, const double *d_params,
                                const sco_settings *s, double *d_x_out, int32_t *d_verdict,
                                double *d_merit, double *d_objective, double *d_max_vio,
                                int32_t *d_stats, void *stream) {
+  return sco_solve_batch_ordered(h, B, d_params, d_x0, s, d_x_out, d_verdict, d_merit, d_objective, d_max_vio,
+                                 d_stats, nullptr, stream);
+}
+
+extern "C" int sco_solve_batch_ordered(sco_handle *h, int64_t B, const double *d_params, const double *d_x0,
+                                       const sco_settings *s, double *d_x_out, int32_t *d_verdict,
+                                       double *d_merit, double *d_objective, double *d_max_vio,
+                                       int32_t *d_stats, const int32_t *d_order, void *stream) {
   if (!h || !s) return fail(SCO_ERR_ARG, "null argument");
   if (B <= 0) return SCO_OK;  // an empty batch is valid and touches nothing
   if (!d_params || !d_x0 || !d_x_out || !d_verdict) return fail(SCO_ERR_ARG, "null argument");
@@ -390,7 +398,7 @@ extern "C" int sco_solve_batch(sco_handle *h, int64_t B, const double *d_params,
   CUDA_TRY(cudaMemsetAsync(h->counter + slot, 0, sizeof(unsigned long long), st));
   const long long grid = std::min<long long>(B, (long long)h->Jscr_ctas);
   SolveArgs a = {(long long)B, d_params, d_x0, d_x_out, d_verdict, d_merit, d_objective, d_max_vio, d_stats,
-                 h->Jscr[slot], h->counter + slot};
+                 h->Jscr[slot], h->counter + slot, d_order};
   h->ops->solve((unsigned)grid, h->smem_bytes, st, h->S, d, a);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(h->slot_done[slot], st));

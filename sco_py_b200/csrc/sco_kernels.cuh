@@ -22,7 +22,7 @@ k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings
         const double *__restrict__ params, const double *__restrict__ x0, double *__restrict__ x_out,
         int *__restrict__ verdict, double *__restrict__ merit, double *__restrict__ objective,
         double *__restrict__ max_vio, int *__restrict__ stats, double *__restrict__ Jscr,
-        unsigned long long *counter) {
+        unsigned long long *counter, const int *__restrict__ order) {
   __shared__ long long next;
   QPW w;
   w.bind(S.L);
@@ -32,9 +32,10 @@ k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings
   while (true) {
     if (tid == 0) next = (long long)atomicAdd(counter, 1ull);
     Team<TEAM>::sync();
-    const long long b = next;
+    const long long slot = next;
     Team<TEAM>::sync();
-    if (b >= B) break;
+    if (slot >= B) break;
+    const long long b = order ? (long long)order[slot] : slot;  // optional processing order (longest first)
     const double *prm = params + b * S.stride;
     SqpSolver<TEAM, DK> sq(S, st, w, prm, Jg);
     SqpOut o = sq.run(x0 + b * S.n);

@@ -14,6 +14,7 @@ struct SolveArgs {
   int *stats;
   double *Jscr;
   unsigned long long *counter;
+  const int *order;
 };
 struct ConvexifyArgs {
   long long B;

@@ -51,7 +51,7 @@ cudaError_t configure(size_t bytes, int *occ) {
 void solve(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, const DevSettings &d,
            const SolveArgs &a) {
   k_solve<T, DK><<<grid, T, smem, st>>>(S, d, a.B, a.params, a.x0, a.x_out, a.verdict, a.merit, a.objective,
-                                    a.max_vio, a.stats, a.Jscr, a.counter);
+                                    a.max_vio, a.stats, a.Jscr, a.counter, a.order);
 }
 #if SCO_DK == 0
 void convexify(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, const ConvexifyArgs &a) {

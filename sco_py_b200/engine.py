@@ -110,8 +110,10 @@ class Engine(object):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ------------------------------------------------------------------ hot path
-    def solve_batch(self, params, x0, settings, stream=None):
+    def solve_batch(self, params, x0, settings, stream=None, order=None):
         """Device-resident solve, enqueued on `stream` (default: torch's current stream).
+        `order`: optional int32 device tensor, a permutation of range(B): the order in which the work
+        queue hands problems out (longest first hides the tail).
         Returns dict of torch tensors (x, verdict, merit, objective, max_vio, stats)."""
         with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
             params, x0 = self._dev(params), self._dev(x0)
@@ -122,9 +124,12 @@ class Engine(object):
             obj = torch.empty_like(merit)
             vio = torch.empty_like(merit)
             stats = torch.empty((B, 4), dtype=torch.int32, device=self.device)
-            _lib.check(self.lib.sco_solve_batch(self.h, B, _ptr(params), _ptr(x0), ctypes.byref(settings),
-                                                _ptr(x), _ptr(verdict), _ptr(merit), _ptr(obj), _ptr(vio),
-                                                _ptr(stats), self._stream()))
+            if order is not None:
+                order = order.to(self.device, torch.int32).contiguous()
+                assert order.numel() == B
+            _lib.check(self.lib.sco_solve_batch_ordered(self.h, B, _ptr(params), _ptr(x0), ctypes.byref(settings),
+                                                        _ptr(x), _ptr(verdict), _ptr(merit), _ptr(obj), _ptr(vio),
+                                                        _ptr(stats), _ptr(order), self._stream()))
         return dict(x=x, verdict=verdict, merit=merit, objective=obj, max_vio=vio, stats=stats)
 
     def solve_batch_host(self, params, x0, settings, out=None, stream=None):

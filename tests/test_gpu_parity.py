@@ -177,6 +177,11 @@ def test_batch_properties_at_scale(engines):
     out2 = eng.solve_batch(params[perm], x0[perm], s)
     assert np.array_equal(out2["x"].cpu().numpy(), x[perm])
     assert np.array_equal(out2["verdict"].cpu().numpy(), verdict[perm])
+    # a processing order (longest first) changes the schedule, not the results
+    import torch
+    order = torch.argsort(out["stats"][:, 2], descending=True).to(torch.int32)
+    out3 = eng.solve_batch(params, x0, s, order=order)
+    assert np.array_equal(out3["x"].cpu().numpy(), x) and np.array_equal(out3["verdict"].cpu().numpy(), verdict)
 
 
 def test_dense_register_path_matches_generic_path(engines):
