@@ -72,13 +72,20 @@ template <int NP, int MP>
 __device__ __forceinline__ int dense_test(const uint32_t sb, const bool rowwarp, const int lane,
                                           const double u0, const double u1, const double u2, const double lo,
                                           const double hi, const DenseState &X, const bool approximate,
-                                          double &pri_out, double &dua_out, int &want_cert) {
+                                          const bool tail, double &pri_out, double &dua_out, int &want_cert) {
   using DL = DenseL<NP, MP>;
   constexpr int LDJ = DL::LDJ;
   const double r0 = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 5)), r1 = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 6));
   const double e0 = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 8)), e1 = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 9));
   const double kd = dense_sc<NP, MP>(sb, 8);
   double v0, v12, v3, v456, nvp, nvd, s0, s1;
+  // Tail mode (the launch's queue is drained, this problem is on the critical path): lane-local parts of
+  // the SECOND stage of the certificates that can only refute them -- mvs = slack columns of |A' dy| / D
+  // (primal), rej = how far A dx leaves the recession cone on slack-bound and box rows (dual).  The first
+  // stage holds in 15-22 % of the tests although these QPs are feasible and bounded; with the two values
+  // almost none of them needs dense_certificates (a lone problem runs 7 % faster; on a full machine the
+  // extra instructions cost 4 %, hence only in tail mode -- profiles/README.md).
+  double mvs = 0.0, rej = 0.0;
   if (rowwarp) {
     const double r2 = lds_f64(dense_la<NP, MP>(sb, true, lane, 7)), e2 = lds_f64(dense_la<NP, MP>(sb, true, lane, 10));
     const uint32_t jr = sb + 8u * (DL::Js + lane * LDJ), xs = sb + 8u * DL::Xs;
@@ -106,6 +113,11 @@ __device__ __forceinline__ int dense_test(const uint32_t sb, const bool rowwarp,
     const double dss = X.s - X.ps;
     nvd = fabs(e2 * dss);
     s1 = u0 * dss;
+    if (tail) {
+      mvs = fabs((u1 * (kd * d1) + u2 * d2) * r2);
+      const double ads = u2 * dss * r1;  // slack-bound row [0, usmax]
+      rej = max_nn(usmax < OSQP_INFTY * OSQP_MIN_SCALING ? ads : 0.0, max_nn(-ads, 0.0));
+    }
   } else {
     const uint32_t pc = sb + 8u * (DL::Ph + lane), jc = sb + 8u * (DL::Js + lane);
     const uint32_t xs = sb + 8u * DL::Xs, ys = sb + 8u * DL::Ys;
@@ -134,10 +146,15 @@ __device__ __forceinline__ int dense_test(const uint32_t sb, const bool rowwarp,
     const double dx = X.p0 - X.pp0;
     nvd = fabs(e1 * dx);
     s1 = u0 * dx;
+    if (tail) {
+      const double adx = u1 * dx * r0;  // box row [lo, hi]
+      rej = max_nn(hi < OSQP_INFTY * OSQP_MIN_SCALING ? adx : 0.0, max_nn(lo > -OSQP_INFTY * OSQP_MIN_SCALING ? -adx : 0.0, 0.0));
+    }
   }
   // one combined team reduction
   v0 = warp_max_nonneg(v0); v12 = warp_max_nonneg(v12); v3 = warp_max_nonneg(v3);
   v456 = warp_max_nonneg(v456); nvp = warp_max_nonneg(nvp); nvd = warp_max_nonneg(nvd);
+  if (tail) { mvs = warp_max_nonneg(mvs); rej = warp_max_nonneg(rej); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -147,8 +164,10 @@ __device__ __forceinline__ int dense_test(const uint32_t sb, const bool rowwarp,
   if (lane == 0) {
     sts_f64(mine, v0); sts_f64(mine + 8u, v12); sts_f64(mine + 16u, v3); sts_f64(mine + 24u, v456);
     sts_f64(mine + 32u, nvp); sts_f64(mine + 40u, nvd); sts_f64(mine + 48u, s0); sts_f64(mine + 56u, s1);
+    if (tail) { sts_f64(mine + 64u, mvs); sts_f64(mine + 72u, rej); }
   }
   __syncthreads();
+  if (tail) { mvs = max_nn(mvs, lds_f64(other + 64u)); rej = max_nn(rej, lds_f64(other + 72u)); }
   v0 = max_nn(v0, lds_f64(other)); v12 = max_nn(v12, lds_f64(other + 8u)); v3 = max_nn(v3, lds_f64(other + 16u));
   v456 = max_nn(v456, lds_f64(other + 24u)); nvp = max_nn(nvp, lds_f64(other + 32u)); nvd = max_nn(nvd, lds_f64(other + 40u));
   // fixed order (rows + variables) so that both warps take the same decision
@@ -168,8 +187,9 @@ __device__ __forceinline__ int dense_test(const uint32_t sb, const bool rowwarp,
   const bool prim_ok = pri_res < eps_p, dual_ok = dua_res < eps_d;
   if (prim_ok && dual_ok) return approximate ? 2 : 1;
   const double epi = f * dense_sc<NP, MP>(sb, 2), edi = f * dense_sc<NP, MP>(sb, 3);
-  if (!prim_ok && nvp > epi && s0 < -epi * nvp) want_cert |= 1;
-  if (!dual_ok && nvd > edi && s1 < -c * edi * nvd) want_cert |= 2;
+  // first stage holds -- and, in tail mode, the lane-local part of the second stage does not refute it
+  if (!prim_ok && nvp > epi && s0 < -epi * nvp && !(tail && mvs >= epi * nvp)) want_cert |= 1;
+  if (!dual_ok && nvd > edi && s1 < -c * edi * nvd && !(tail && rej > edi * nvd)) want_cert |= 2;
   return 0;
 }
 
@@ -333,7 +353,7 @@ __device__ __noinline__ int dense_final_tests(const uint32_t sb, const int n, co
   __syncthreads();
   for (int approx = checked ? 1 : 0; approx < 2; approx++) {
     int cert;
-    int status = dense_test<NP, MP>(sb, rowwarp, lane, L.u0, L.u1, L.u2, L.lo, L.hi, X, approx != 0, pri, dua, cert);
+    int status = dense_test<NP, MP>(sb, rowwarp, lane, L.u0, L.u1, L.u2, L.lo, L.hi, X, approx != 0, true, pri, dua, cert);
     if (status == 0 && cert) {
       const int r = dense_certificates<NP, MP>(sb, n, m, approx != 0, (cert & 1) != 0, (cert & 2) != 0);
       if (r & 1) status = approx ? 3 : -3;
@@ -369,6 +389,7 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
   const double rho = fmin(fmax(st_.rho, OSQP_RHO_MIN), OSQP_RHO_MAX), rhoi = 1.0 / rho;
   const int max_iter = st_.max_iter, chk = st_.check_termination, scaling = st_.scaling;
   const double pi = a_.pi, kd = a_.kd;
+  const bool tail = a_.tail != 0;
   const double *__restrict__ Jg = a_.Jg;
   const double *__restrict__ Qg = field_ptr(S_, S_.Q, a_.prm);
   const double *__restrict__ qg = field_ptr(S_, S_.q, a_.prm);
@@ -718,7 +739,7 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
     sts_f64(my_chk, rowwarp ? kd * X.y0 : X.p0);
     __syncthreads();
     int cert;
-    status = dense_test<NP, MP>(sb, rowwarp, lane, u0, u1, u2, lo, hi, X, false, res.pri_res, res.dua_res, cert);
+    status = dense_test<NP, MP>(sb, rowwarp, lane, u0, u1, u2, lo, hi, X, false, tail, res.pri_res, res.dua_res, cert);
 #ifdef SCO_SKIP_PROBE
     {  // experiment: how often would a lane-local lower bound of the primal residual already decide "not converged"?
       const double r0p = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 5)), r1p = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 6));

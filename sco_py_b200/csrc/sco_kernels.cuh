@@ -38,6 +38,8 @@ k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings
     const long long b = order ? (long long)order[slot] : slot;  // optional processing order (longest first)
     const double *prm = params + b * S.stride;
     SqpSolver<TEAM, DK> sq(S, st, w, prm, Jg);
+    sq.queue = counter;
+    sq.queue_len = B;
     SqpOut o = sq.run(x0 + b * S.n);
     for (int j = tid; j < S.n; j += TEAM) x_out[b * S.n + j] = xc[j];
     if (tid == 0) {
@@ -126,6 +128,7 @@ k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st
     a.use_pen = use_pen;
     a.closest = closest;
     a.has_hq = 0;
+    a.tail = 0;
     QPSolver<TEAM, DK> qp(S, st, w, a);
     QPResult r = qp.solve();
     const int nq = use_pen ? S.n_q : n;

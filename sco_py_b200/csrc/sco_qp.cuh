@@ -30,6 +30,7 @@ struct QPArgs {
   int use_pen;        // 0: no penalty rows / slacks (closest feasible point)
   int closest;        // objective |x - xs|^2
   int has_hq;         // add the degree-2 model of a non-quadratic objective term (w.Hq, w.gq)
+  int tail;           // the launch's work queue is drained: favour the latency of this problem (sco_dense.cuh)
 };
 
 struct QPResult {

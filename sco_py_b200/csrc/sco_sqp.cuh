@@ -30,6 +30,9 @@ struct SqpSolver {
   Sh xc;        // current iterate (shared memory)
   double *Jg;   // unscaled Jacobian entries of the last convexification (global scratch)
   const int tid, n, m_nl, ng;
+  // work queue of the launch (k_solve): once it is drained the remaining problems decide when the launch ends
+  const unsigned long long *queue = nullptr;
+  long long queue_len = 0;
 
   __device__ SqpSolver(const DevStruct &S_, const DevSettings &st_, QPW &w_, const double *prm_,
                        double *Jg_)
@@ -223,7 +226,7 @@ struct SqpSolver {
       for (int j = tid; j < n; j += TEAM) { w.xs[j] = xc[j]; w.lb[j] = -INFINITY; w.ub[j] = INFINITY; }
       sync();
       QPArgs a;
-      a.prm = prm; a.Jg = nullptr; a.pi = 0.0; a.kd = 0.0; a.use_pen = 0; a.closest = 1; a.has_hq = 0;
+      a.prm = prm; a.Jg = nullptr; a.pi = 0.0; a.kd = 0.0; a.use_pen = 0; a.closest = 1; a.has_hq = 0; a.tail = 0;
       DevSettings d = st;
       d.eps_abs = 1e-6; d.eps_rel = 1e-9; d.max_iter = 100000; d.rho = 0.1; d.sigma = 5e-10;
       d.adaptive_rho = 0;
@@ -270,6 +273,13 @@ struct SqpSolver {
             sync();
             QPArgs a;
             a.prm = prm; a.Jg = Jg; a.pi = pi; a.kd = kd; a.use_pen = 1; a.closest = 0; a.has_hq = S.obj_len != 0;
+            // one thread looks at the queue and the team agrees on the answer (a per-thread read could
+            // split the team at the moment the queue runs dry)
+            if (tid == 0)
+              w.red[0] = (queue && *(const volatile unsigned long long *)queue >= (unsigned long long)queue_len) ? 1.0 : 0.0;
+            sync();
+            a.tail = w.red[0] != 0.0;
+            sync();
             QPSolver<TEAM, DK> qp(S, st, w, a);
             QPResult r = qp.solve();
             o.qp_solves++; o.admm_iters += r.iters; o.last_status = r.status;
