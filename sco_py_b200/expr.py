@@ -51,6 +51,33 @@ def _central_jacobian(fun, x):
     return J
 
 
+HESS_BASE_STEP = np.finfo(float).eps ** (1.0 / 7.8)  # numdifftools default for second derivatives
+
+
+def _central_hessian(fun, x):
+    """(n, n) Hessian of a scalar fun at flat x: central second differences at h and 2h,
+    Richardson-combined -- the scheme of the device kernel (sco_families.cuh vm_fd2)."""
+    x = np.asarray(x, dtype=float).ravel()
+    n = x.size
+    f = lambda v: float(np.ravel(fun(v))[0])
+    f0 = f(x)
+    h0 = HESS_BASE_STEP * np.maximum(np.log1p(np.abs(x)), 1.0)
+    est = []
+    for mult in (1.0, 2.0):
+        h = h0 * mult
+        H = np.zeros((n, n))
+        for i in range(n):
+            ei = np.zeros(n)
+            ei[i] = h[i]
+            H[i, i] = (f(x + 2 * ei) - 2.0 * f0 + f(x - 2 * ei)) / (4.0 * h[i] * h[i])
+            for j in range(i + 1, n):
+                ej = np.zeros(n)
+                ej[j] = h[j]
+                H[i, j] = H[j, i] = (f(x + ei + ej) - f(x + ei - ej) - f(x - ei + ej) + f(x - ei - ej)) / (4.0 * h[i] * h[j])
+        est.append(H)
+    return (4.0 * est[0] - est[1]) / 3.0
+
+
 class Expr(object):
     """Black-box expression f with optional analytic gradient / Hessian (expr.py:22-156)."""
 
@@ -87,9 +114,7 @@ class Expr(object):
         return self._num_hess(x)
 
     def _num_hess(self, x):
-        flat = self._flat(x)
-        H = _central_jacobian(lambda v: _central_jacobian(flat, v)[0], x)
-        return 0.5 * (H + H.T)
+        return _central_hessian(self._flat(x), x)
 
     def convexify(self, x, degree=1):
         """Affine (degree 1) or convex quadratic (degree 2) model at x (expr.py:130-156)."""
