@@ -63,3 +63,34 @@ def test_engine_refuses_to_run_without_a_gpu():
     h = ctypes.c_void_p()
     rc = lib.sco_create(ctypes.byref(cs), 0, ctypes.byref(h))
     assert rc == -2 and b"no CUDA device" in lib.sco_last_error()
+
+
+def test_c_example_compiles_links_and_refuses_to_run_without_a_gpu():
+    """examples/solve_qcqp.c: a C host needs nothing but include/sco_b200.h and the shared library; on a
+    machine without a CUDA device sco_create fails with a message (no CPU fallback)."""
+    import shutil
+    import subprocess
+    from sco_py_b200 import _lib, build
+    build.build()
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = os.path.join(ROOT, "examples", "solve_qcqp")
+    cmd = ["gcc", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "solve_qcqp.c"), "-o", exe,
+           _lib.LIB_PATH, "-lm", "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)]
+    subprocess.check_call(cmd)
+    import torch
+    if not torch.cuda.is_available():
+        p = subprocess.run([exe, "4"], capture_output=True, text=True)
+        assert p.returncode == 1 and "no CUDA device" in p.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_runs():
+    import subprocess
+    from sco_py_b200 import _lib
+    exe = os.path.join(ROOT, "examples", "solve_qcqp")
+    subprocess.check_call(["gcc", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "solve_qcqp.c"),
+                           "-o", exe, _lib.LIB_PATH, "-lm", "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)])
+    p = subprocess.run([exe, "64"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "converged" in p.stdout
