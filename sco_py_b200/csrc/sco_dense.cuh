@@ -88,7 +88,9 @@ __device__ __forceinline__ int dense_test(const uint32_t sb, const bool rowwarp,
   double mvs = 0.0, rej = 0.0;
   if (rowwarp) {
     const double r2 = lds_f64(dense_la<NP, MP>(sb, true, lane, 7)), e2 = lds_f64(dense_la<NP, MP>(sb, true, lane, 10));
-    const uint32_t jr = sb + 8u * (DL::Js + lane * LDJ), xs = sb + 8u * DL::Xs;
+    // lanes beyond the padded row / column count read row / column 0: what lies behind the matrices may
+    // be stale shared memory (a NaN pattern times their zero scale factor would still be NaN)
+    const uint32_t jr = sb + 8u * (DL::Js + (lane < MP ? lane : 0) * LDJ), xs = sb + 8u * DL::Xs;
     double a0 = 0.0, a1 = 0.0;
 #pragma unroll 2
     for (int k = 0; k < NP; k += 2) {
@@ -119,7 +121,8 @@ __device__ __forceinline__ int dense_test(const uint32_t sb, const bool rowwarp,
       rej = max_nn(usmax < OSQP_INFTY * OSQP_MIN_SCALING ? ads : 0.0, max_nn(-ads, 0.0));
     }
   } else {
-    const uint32_t pc = sb + 8u * (DL::Ph + lane), jc = sb + 8u * (DL::Js + lane);
+    const int col = lane < NP ? lane : 0;
+    const uint32_t pc = sb + 8u * (DL::Ph + col), jc = sb + 8u * (DL::Js + col);
     const uint32_t xs = sb + 8u * DL::Xs, ys = sb + 8u * DL::Ys;
     const double ax = u1 * X.p0;
     v0 = fabs((ax - X.z0) * r0);
@@ -281,7 +284,7 @@ __device__ __noinline__ int dense_certificates(const uint32_t sb, const int n, c
         mv = fabs((L.u1 * (kd * d1) + L.u2 * d2) * L.r2);
       } else {
         double t = 0.0;
-        for (int i = 0; i < MP; i++) t = fma(lds_f64(sb + 8u * (DL::Js + i * LDJ + lane)), lds_f64(sb + 8u * (DL::Ys + i)), t);
+        for (int i = 0; i < MP; i++) t = fma(lds_f64(sb + 8u * (DL::Js + i * LDJ + (lane < NP ? lane : 0))), lds_f64(sb + 8u * (DL::Ys + i)), t);
         mv = fabs((t + L.u1 * d3) * L.r1);
       }
       dense_team2<NP, MP>(sb, rowwarp, lane, mv, dummy);
@@ -307,7 +310,7 @@ __device__ __noinline__ int dense_certificates(const uint32_t sb, const int n, c
       double pv = 0.0, dummy = 0.0;
       if (!rowwarp) {  // |c Psym (D dx)|_j = |(Ph dx)_j / D_j|
         double t = 0.0;
-        for (int k = 0; k < NP; k++) t = fma(lds_f64(sb + 8u * (DL::Ph + k * NP + lane)), lds_f64(sb + 8u * (DL::Xs + k)), t);
+        for (int k = 0; k < NP; k++) t = fma(lds_f64(sb + 8u * (DL::Ph + k * NP + (lane < NP ? lane : 0))), lds_f64(sb + 8u * (DL::Xs + k)), t);
         pv = fabs(t * L.r1);
       }
       dense_team2<NP, MP>(sb, rowwarp, lane, pv, dummy);
@@ -316,7 +319,7 @@ __device__ __noinline__ int dense_certificates(const uint32_t sb, const int n, c
         double bad = 0.0;
         if (rowwarp) {
           double t = 0.0;
-          for (int k = 0; k < NP; k++) t = fma(lds_f64(sb + 8u * (DL::Js + lane * LDJ + k)), lds_f64(sb + 8u * (DL::Xs + k)), t);
+          for (int k = 0; k < NP; k++) t = fma(lds_f64(sb + 8u * (DL::Js + (lane < MP ? lane : 0) * LDJ + k)), lds_f64(sb + 8u * (DL::Xs + k)), t);
           const double adx = (t + L.u1 * dss) * L.r0;
           const double lpl = -OSQP_INFTY * L.e0, usmax = OSQP_INFTY * L.e1;
           if (act && ((L.hi < OSQP_INFTY * OSQP_MIN_SCALING && adx > lim) ||
