@@ -206,10 +206,17 @@ class PortProblem(object):
             self.b.append(bb)
 
     def update_obj(self, mu):  # prob.py:414-426
-        if self.masks is None:  # _lazy_spawn_osqp_cnts, prob.py:434-444
-            self.masks = [(J != 0.0) for J in self.J]
-        self.kdup += 1
-        self.pi *= mu
+        # `quirks` switches the OSQP-backend behaviours off one by one ("intended semantics", the
+        # maths of the Gurobi backend: sco_gurobi/prob.py:316-318,365-373): fixed weight, fresh
+        # sparsity, single copy of the penalty rows
+        q = getattr(self, "quirks", None) or {}
+        if q.get("freeze_sparsity", True):
+            if self.masks is None:  # _lazy_spawn_osqp_cnts, prob.py:434-444
+                self.masks = [(J != 0.0) for J in self.J]
+        else:
+            self.masks = [np.ones_like(J, dtype=bool) for J in self.J]
+        self.kdup = self.kdup + 1 if q.get("duplicate_rows", True) else 1
+        self.pi = self.pi * mu if q.get("compound_penalty", True) else mu
 
     # -- QP ------------------------------------------------------------------
     def solve_qp(self, lbx, ubx, penalty, osqp_kw, P_override=None, q_override=None):
@@ -289,13 +296,14 @@ class PortProblem(object):
                              q_override=-2.0 * x0)
 
 
-def solve(st, row, x0, solver=None, osqp_kw=None, max_sqp_iters=10000, keep_trace=False):
+def solve(st, row, x0, solver=None, osqp_kw=None, max_sqp_iters=10000, keep_trace=False, quirks=None):
     """Returns dict(x, success, merit, objective, max_vio, stats, trace)."""
     S = dict(DEFAULT_SOLVER)
     S.update(solver or {})
     O = dict(DEFAULT_OSQP)
     O.update(osqp_kw or {})
     p = PortProblem(st, row, x0)
+    p.quirks = quirks
     delta0 = S["initial_trust_region_size"]
     mu = S["initial_penalty_coeff"]
     delta = delta0

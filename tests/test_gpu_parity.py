@@ -236,3 +236,18 @@ def test_adaptive_rho_reaches_the_same_qp_optimum(engines):
             res = helpers.oracle_qp(P, q, A, l, u, adaptive_rho=True)
             assert status[i] in (1, 2) and res.info.status_val in (1, 2), (name, i, status[i], res.info.status_val)
             assert np.abs(xq[i] - res.x).max() <= 1e-5 * max(1.0, np.abs(res.x).max()), (name, i)
+
+
+def test_intended_semantics_mode_matches_the_port(engines):
+    """The OSQP-backend quirks switched off (compound_penalty = freeze_sparsity = duplicate_rows = 0:
+    fixed penalty weight, fresh sparsity, one copy of the penalty rows -- the maths of the reference's
+    Gurobi backend): device against the port with the same switches, and the
+    default penalty coefficient 1e3 of Solver() becomes usable (with the quirks it drives |q| to 1e18)."""
+    eng, st, params, x0 = engines["qcqp"]
+    off = dict(compound_penalty=0, freeze_sparsity=0, duplicate_rows=0)
+    out = eng.solve_batch(params, x0, _settings(**off))
+    x, verdict = out["x"].cpu().numpy(), out["verdict"].cpu().numpy()
+    for i in range(x0.shape[0]):
+        ref = sqp_port.solve(st, params[i], x0[i], solver=W.SOLVER_SETTINGS, quirks={k: False for k in off})
+        assert (verdict[i] == 1) == ref["success"], i
+        assert np.abs(x[i] - ref["x"]).max() <= 1e-4 * max(1.0, np.abs(ref["x"]).max()), i
