@@ -9,18 +9,26 @@ batch of B synthetic problems per GPU.  Workload = BASELINE.json configs[3]: C4 
 n=20, m=30, problem i drawn from default_rng(4000+i) (sco_py_b200/workloads.py), B=65,536 per GPU
 ("weak" scaling: rank r solves problems [r*B, (r+1)*B), no data-path collective).
 `value` is timed with inputs resident in HBM; `e2e` is the same batch through the host-buffer
-C-ABI entry (sco_solve_batch_host) from pinned memory, copies inside the timed region.
+C-ABI entry (sco_solve_batch_host_async) from pinned memory, copies inside the timed region, for the
+same number of steps.  After the timed regions (never inside them) the run
+  * audits a random subsample of the batch against the CPU oracle (`detail.audit`; the same CPU pass
+    is the `cpu_baseline` sample), and
+  * times the two trajectory configurations, C2 point robot B=1,024 and C3 arm B=4,096
+    (`detail.other_configs`, each with its own roofline and audit).
 
 Reference arm (--impl reference): the reference's algorithm on the host CPUs -- the oracle port
-(oracle/sqp_port.py + oracle/osqp_core.c, bit-identical to /root/reference's sco_py run on the
-oracle shims; upstream OSQP is not installable in this image) -- one process per core, each step
-a bounded sample of the same workload.
+(oracle/sqp_port.py + oracle/osqp_core.c, equal to /root/reference's sco_py run on the oracle shims;
+upstream OSQP is not installable in this image) -- one process per core, bounded by WALL CLOCK: problems
+are dealt one at a time until the budget (SCO_REF_BUDGET_S, default 150 s) is spent; whatever is still
+running then is abandoned and value = converged problems / elapsed.  A single problem can need tens of
+minutes on a core (penalty SQP has no iteration cap), so a sample bounded by count never ends in time.
 
 Under torchrun (WORLD_SIZE > 1) every rank runs its shard; rank 0 prints ONE JSON line.
 """
 import argparse
 import json
 import os
+import signal
 import subprocess
 import sys
 import threading
@@ -34,6 +42,12 @@ import numpy as np  # noqa: E402
 
 METRIC = "converged SQP problems/sec"
 UNIT = "problems/s"
+CONFIG_NAMES = {"qcqp": "C4 non-convex QCQP n=20 m=30 (BASELINE.json configs[3]), rng seeds 4000+i",
+                "point_robot": "C2 point robot T=40 K=3 (configs[1]), rng seeds 2000+i",
+                "arm": "C3 7-DOF arm T=20 (configs[2]), rng seeds 3000+i"}
+PORT_NOTE = ("oracle port = the reference's penalty-SQP restated on structured inputs + restated OSQP 0.6.2 "
+             "(equal to /root/reference run on the oracle shims to 1e-8, tests/test_oracle.py; upstream OSQP is "
+             "not installable in this image)")
 
 
 # ------------------------------------------------------------------------------ CPU arm
@@ -41,26 +55,29 @@ def _cpu_init():
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "shims")):
         if p not in sys.path:
             sys.path.insert(0, p)
+    signal.signal(signal.SIGTERM, signal.SIG_DFL)
     try:
         from threadpoolctl import threadpool_limits
         threadpool_limits(1)
     except Exception:
         pass
+    import sqp_port  # noqa: F401  (import cost outside the timed region)
 
 
 def _cpu_solve_one(job):
     name, index = job
-    _cpu_init()
     import sqp_port
     from sco_py_b200 import workloads as W
     st, params, x0 = W.GENERATORS[name](1, first=index)
     t0 = time.time()
     r = sqp_port.solve(st, params[0], x0[0], solver=W.SOLVER_SETTINGS)
-    return index, bool(r["success"]), time.time() - t0, r["stats"]["qp_solves"], r["stats"]["admm_iters"]
+    return dict(index=index, success=bool(r["success"]), seconds=time.time() - t0, x=r["x"],
+                max_vio=float(r["max_vio"]), objective=float(r["objective"]),
+                qp_solves=int(r["stats"]["qp_solves"]), admm_iters=int(r["stats"]["admm_iters"]))
 
 
 class CpuArm(object):
-    """The oracle port on every host core, one process per core."""
+    """The oracle port on every host core, one process per core, bounded by wall clock."""
 
     def __init__(self, name, cores=None):
         import multiprocessing as mp
@@ -70,68 +87,107 @@ class CpuArm(object):
         import build as oracle_build
         oracle_build.build()
         self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init)
-        self.next_index = 0
+        self.pool.map(abs, range(self.cores * 4))  # workers up, imports done
 
-    def sample(self, count):
-        jobs = [(self.name, self.next_index + i) for i in range(count)]
-        self.next_index += count
+    def run(self, indices, budget_s, on_result=None):
+        """Deals `indices` one at a time; stops at the deadline.  -> dict(results, wall, dealt, complete)."""
+        jobs = [(self.name, int(i)) for i in indices]
         t0 = time.time()
-        res = self.pool.map(_cpu_solve_one, jobs, chunksize=1)
+        it = self.pool.imap_unordered(_cpu_solve_one, jobs, chunksize=1)
+        results = []
+        complete = False
+        import multiprocessing as mp
+        while True:
+            left = budget_s - (time.time() - t0)
+            if left <= 0:
+                break
+            try:
+                r = it.next(timeout=left)
+            except mp.TimeoutError:
+                break
+            except StopIteration:
+                complete = True
+                break
+            results.append(r)
+            if on_result is not None:
+                on_result(r, time.time() - t0)
         wall = time.time() - t0
-        conv = sum(1 for r in res if r[1])
-        return dict(wall=wall, problems=count, converged=conv,
-                    admm_iters=sum(r[4] for r in res), qp_solves=sum(r[3] for r in res))
+        return dict(results=results, wall=wall, dealt=len(jobs), complete=complete)
 
     def close(self):
-        self.pool.close()
+        self.pool.terminate()  # abandons whatever is still running
         self.pool.join()
+
+
+def reference_line(args, value, conv, done, wall, cores, sample):
+    return {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, args.config, args.batch),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "detail": {"converged": conv, "problems_completed": done, "wall_s": wall},
+    }
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    budget = float(os.environ.get("SCO_REF_BUDGET_S", "150"))
     arm = CpuArm(args.config, args.cpu_cores)
-    per_step = args.cpu_sample or 2 * arm.cores  # two per core, dealt dynamically: the slowest problem sets the wall
-    for _ in range(args.warmup):
-        arm.sample(per_step)
-    tot_wall, tot_conv, tot_prob = 0.0, 0, 0
-    for _ in range(args.steps):
-        s = arm.sample(per_step)
-        tot_wall += s["wall"]
-        tot_conv += s["converged"]
-        tot_prob += s["problems"]
+    state = dict(conv=0, done=0, wall=0.0, printed=False, t0=time.time())
+
+    def emit():
+        if state["printed"]:
+            return
+        state["printed"] = True
+        wall = max(state["wall"], 1e-9)
+        sample = ("problems 0.. of the %s workload dealt one at a time to %d processes for %.0f s of wall clock (no "
+                  "warm-up: a process pool has none); %d completed, the ones still running at the deadline are "
+                  "abandoned and not counted; %s" % (args.config, arm.cores, wall, state["done"], PORT_NOTE))
+        print(json.dumps(reference_line(args, state["conv"] / wall, state["conv"], state["done"], wall, arm.cores, sample)))
+        sys.stdout.flush()
+
+    def on_result(r, elapsed):
+        state["done"] += 1
+        state["conv"] += 1 if r["success"] else 0
+        state["wall"] = elapsed
+
+    def on_term(signum, frame):  # the driver's timeout: report what has been measured so far
+        state["wall"] = time.time() - state["t0"]
+        emit()
+        try:
+            arm.pool.terminate()
+        except Exception:
+            pass
+        os._exit(0)
+
+    signal.signal(signal.SIGTERM, on_term)
+    signal.signal(signal.SIGINT, on_term)
+    state["t0"] = time.time()
+    out = arm.run(range(0, arm.cores * 256), budget, on_result)
+    state["wall"] = out["wall"]
+    emit()
     arm.close()
-    value = tot_conv / tot_wall
-    sample = ("%d problems per step (two per core, dynamic), problems 0..%d of the %s workload over warm-up + timed "
-              "steps, oracle port = reference algorithm on restated OSQP (upstream OSQP not installable here)"
-              % (per_step, arm.next_index - 1, args.config))
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_wall / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args, args.batch),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
     return 0
 
 
 # ------------------------------------------------------------------------------ helpers
-def workload_config(args, per_gpu_batch):
-    names = {"qcqp": "C4 non-convex QCQP n=20 m=30 (BASELINE.json configs[3]), rng seeds 4000+i",
-             "point_robot": "C2 point robot T=40 K=3 (configs[1]), rng seeds 2000+i",
-             "arm": "C3 7-DOF arm T=20 (configs[2]), rng seeds 3000+i"}
-    return {"workload": names[args.config], "batch_per_gpu": per_gpu_batch,
+def workload_config(args, name, per_gpu_batch):
+    n_streams = max(1, min(getattr(args, "streams", 1), 8))
+    return {"workload": CONFIG_NAMES[name], "batch_per_gpu": per_gpu_batch,
             "global_batch": per_gpu_batch * args.gpus, "parallelism": "problems sharded, dp%d" % args.gpus,
-            "pipelining": "steps (independent batches) round-robin over %d CUDA streams" % max(1, min(getattr(args, "streams", 1), 4)),
+            "pipelining": "steps (independent batches) round-robin over %d CUDA streams" % n_streams,
             "queue_order": getattr(args, "order", "index"),
             "solver": "penalty_sqp, test_solver.py:15-25 hyper-parameters (mu0=1), OSQP eps_abs 1e-6 eps_rel 1e-9 "
-                      "rho 0.1 fixed, reference quirks C-1..C-3 on",
+                      "rho 0.1 fixed, reference quirks C-1..C-4 on, cold-started QPs",
             "l2": "inputs (%.2f GB of parameters per GPU) exceed the 126 MB L2; no flush needed"
-                  % (per_gpu_batch * 58800 / 1e9) if args.config == "qcqp" else "inputs exceed L2 at the default batch"}
+                  % (per_gpu_batch * 58800 / 1e9) if name == "qcqp" else
+                  "parameters are small (L2-resident after the first step, as they are for the reference's CPU "
+                  "caches); the kernel's working set lives in shared memory"}
 
 
 class ClockSampler(object):
@@ -212,13 +268,204 @@ def admm_flops(st, stats):
     return float(stats[:, 2].astype(np.float64).sum() * per_iter), per_iter
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def roofline_of(name, st, stats, ms_step, fp64_peak, B):
+    """The dominant (only) kernel of a step is k_solve.  Its working set is resident in shared memory, so the
+    binding resource is the FP64 pipe; the HBM view SURVEY.md 8(d) asks for is reported beside it."""
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    abytes, b_qp, b_cvx = algorithmic_bytes(st, stats)
+    flops, per_iter = admm_flops(st, stats)
+    achieved_tf = flops / (ms_step * 1e-3) / 1e12
+    achieved_gbs = abytes / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(name, {}).get("dram_bytes_per_problem")
+            if traffic is not None:
+                traffic = traffic * B
+        except Exception:
+            traffic = None
+    return {
+        "kernel": "k_solve (fused convexify + penalty-QP assembly + ADMM + merit/trust-region, one launch per step)",
+        "regime": "resident: the whole QP working set lives in shared memory / registers for the solve",
+        "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": achieved_tf / fp64_peak if fp64_peak else None,
+        "peak_source": "sco_probe_fp64: dependent-free DFMA loop measured in this run (MEASURED_PEAKS.json carries no FP64 "
+                       "figure; nominal 64 FMA/clk/SM x 148 SMs x 1.965 GHz = 37.2 TFLOP/s)",
+        "flops_per_admm_iter": per_iter, "traffic": traffic,
+        "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes, "bytes_per_qp": b_qp,
+                "bytes_per_convexification": b_cvx,
+                "note": "SURVEY.md 8(d) formula; small by construction in the resident regime (DESIGN.md section 4)"},
+    }
+
+
+def audit_against_oracle(name, indices, dev, budget_s, cores, first=0):
+    """Solves problems `indices` (batch-local) of config `name` with the CPU oracle, for at most `budget_s` of wall
+    clock, and compares them with the device results `dev` (numpy dict of the whole batch).
+    -> (audit dict, cpu_baseline dict)."""
+    arm = CpuArm(name, cores)
+    out = arm.run([first + int(i) for i in indices], budget_s)
+    arm.close()
+    res = out["results"]
+    rel, dvio, dobj, match, conv = [], [], [], 0, 0
+    for r in res:
+        i = r["index"] - first
+        ok_dev = bool(dev["verdict"][i] == 1)
+        match += int(ok_dev == r["success"])
+        conv += int(r["success"])
+        rel.append(float(np.abs(dev["x"][i] - r["x"]).max() / max(1.0, np.abs(r["x"]).max())))
+        dvio.append(abs(float(dev["max_vio"][i]) - r["max_vio"]))
+        dobj.append(abs(float(dev["objective"][i]) - r["objective"]) / max(1.0, abs(r["objective"])))
+    n = len(res)
+    audit = {"problems": n, "requested": len(indices), "budget_s": budget_s, "complete": out["complete"],
+             "selection": "random subsample of the batch (rng 12345), dealt in that order; problems still running at the "
+                          "deadline are dropped",
+             "verdict_match": match, "converged_on_cpu": conv,
+             "rel_dx": {"p50": float(np.percentile(rel, 50)) if n else None, "p99": float(np.percentile(rel, 99)) if n else None,
+                        "max": max(rel) if n else None},
+             "dvio_max": max(dvio) if n else None, "dobj_rel_max": max(dobj) if n else None,
+             "tolerance": "north_star: 1e-4 relative on x, 1e-5 absolute on violation, same verdict"}
+    cpu = {"value": conv / out["wall"] if out["wall"] > 0 else None, "unit": UNIT, "cores": arm.cores, "kind": "port",
+           "sample": "%d random problems of the same batch completed in %.1f s of wall clock on %d processes (the audit "
+                     "pass; unfinished ones dropped); %s" % (n, out["wall"], arm.cores, PORT_NOTE),
+           "admm_iters_per_problem": float(np.mean([r["admm_iters"] for r in res])) if n else None}
+    return audit, cpu
+
+
 # ------------------------------------------------------------------------------ GPU arm
+def time_config(args, name, B, steps, warmup, dev, local, rank, world, dist, sampler_on, e2e=True):
+    """Generates config `name` (problems [rank*B, (rank+1)*B)), times `steps` device-resident steps and the same number
+    of end-to-end steps.  -> dict of measurements + host copies of the results."""
+    import torch
+    from sco_py_b200 import workloads as W
+    from sco_py_b200.engine import Engine, make_settings
+    t_gen = time.time()
+    st0 = W.GENERATORS[name](1)[0]
+    h_params = torch.empty((B, st0.stride), dtype=torch.float64, pin_memory=True)
+    h_x0 = torch.empty((B, st0.n), dtype=torch.float64, pin_memory=True)
+    st, _, _ = W.gen_batch(name, B, first=rank * B, out_params=h_params.numpy(), out_x0=h_x0.numpy())
+    t_gen = time.time() - t_gen
+    eng = Engine(st, device=local)
+    settings = make_settings(solver=W.SOLVER_SETTINGS)
+    d_params = h_params.to(dev, non_blocking=True)
+    d_x0 = h_x0.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    # Steps are independent batches: they are pipelined over `--streams` CUDA streams (launch slots of the
+    # handle), so the tail of one launch -- a few long problems on a handful of SMs -- overlaps the next
+    # launches.  The timed region is still K whole steps.
+    n_streams = max(1, min(args.streams, 8))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    cur = torch.cuda.current_stream(dev)
+    order = [None]
+
+    def run_steps(count):
+        outs = []
+        for s_ in streams:
+            s_.wait_stream(cur)
+        for i in range(count):
+            outs.append(eng.solve_batch(d_params, d_x0, settings, stream=streams[i % n_streams], order=order[0]))
+        for s_ in streams:
+            cur.wait_stream(s_)
+        return outs
+
+    warm = run_steps(warmup)
+    if args.order == "profile" and warm:
+        torch.cuda.synchronize()
+        order[0] = torch.argsort(warm[-1]["stats"][:, 2], descending=True).to(torch.int32)
+        run_steps(1)
+    del warm
+    barrier()
+    sampler = ClockSampler(local) if sampler_on else None
+    if sampler is not None:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    outs = run_steps(steps)
+    e1.record(cur)
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    ms_total = reduce(ms_local, dist.ReduceOp.MAX if world > 1 else None)
+    clocks = sampler.stop() if sampler is not None else None
+    out = outs[-1]
+    for o_ in outs[:-1]:
+        if not torch.equal(o_["verdict"], out["verdict"]) or not torch.equal(o_["x"], out["x"]):
+            raise SystemExit("bench.py: two steps over the same batch disagree")
+    host = {k: v.cpu().numpy() for k, v in out.items()}
+    del outs
+    verdict, stats = host["verdict"], host["stats"]
+    converged = reduce(float((verdict == 1).sum()), dist.ReduceOp.SUM if world > 1 else None)
+    res = dict(st=st, eng=eng, host=host, ms_local=ms_local, ms_total=ms_total, clocks=clocks, converged=converged,
+               value=converged * steps / (ms_total * 1e-3), t_gen=t_gen, n_streams=n_streams, B=B)
+
+    if e2e:
+        # end-to-end: host buffers through the C ABI (sco_solve_batch_host_async), the H2D copy of every step's
+        # inputs and the D2H copy of its results inside the timed region, same pipelining, same number of steps
+        def host_out():
+            return dict(x=torch.empty((B, st.n), dtype=torch.float64, pin_memory=True).numpy(),
+                        verdict=torch.empty(B, dtype=torch.int32, pin_memory=True).numpy(),
+                        merit=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
+                        objective=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
+                        max_vio=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
+                        stats=torch.empty((B, 4), dtype=torch.int32, pin_memory=True).numpy())
+
+        e2e_steps = max(1, min(steps, args.e2e_steps if args.e2e_steps > 0 else steps))
+        h_outs = [host_out() for _ in range(min(e2e_steps, n_streams))]
+
+        def run_e2e(count):
+            for i in range(count):
+                eng.solve_batch_host(h_params.numpy(), h_x0.numpy(), settings, out=h_outs[i % len(h_outs)],
+                                     stream=streams[i % n_streams])
+            for s_ in streams:
+                s_.synchronize()
+
+        run_e2e(min(len(h_outs), 2))  # warm-up (staging allocations)
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(e2e_steps)
+        barrier()
+        e2e_s = reduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+        e2e_conv = reduce(float((h_outs[0]["verdict"] == 1).sum()), dist.ReduceOp.SUM if world > 1 else None)
+        for ho in h_outs:
+            if not np.array_equal(ho["verdict"], verdict) or not np.array_equal(ho["x"], host["x"]):
+                raise SystemExit("bench.py: host-buffer path and device path disagree")
+        res["e2e"] = {"value": e2e_conv * e2e_steps / e2e_s, "unit": UNIT,
+                      "h2d_bytes_per_step": h_params.numel() * 8 + h_x0.numel() * 8,
+                      "d2h_bytes_per_step": sum(v.nbytes for v in h_outs[0].values()),
+                      "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps}
+        del h_outs
+    del d_params, d_x0, h_params, h_x0
+    return res
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
     from sco_py_b200 import _lib
-    from sco_py_b200 import workloads as W
-    from sco_py_b200.engine import Engine, make_settings
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -237,204 +484,84 @@ def run_b200_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    t_gen = time.time()
-    # pinned host staging for the end-to-end leg
-    st0 = W.GENERATORS[args.config](1)[0]
-    h_params = torch.empty((B, st0.stride), dtype=torch.float64, pin_memory=True)
-    h_x0 = torch.empty((B, st0.n), dtype=torch.float64, pin_memory=True)
-    st, _, _ = W.gen_batch(args.config, B, first=rank * B, out_params=h_params.numpy(), out_x0=h_x0.numpy())
-    t_gen = time.time() - t_gen
-    eng = Engine(st, device=local)
-    settings = make_settings(solver=W.SOLVER_SETTINGS)
-    d_params = h_params.to(dev, non_blocking=True)
-    d_x0 = h_x0.to(dev, non_blocking=True)
-    torch.cuda.synchronize()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def reduce_max(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def reduce_sum(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    # ---- device-resident leg.  Steps are independent batches: they are pipelined over `--streams`
-    # CUDA streams (launch slots of the handle), so the tail of one launch -- a few long problems on
-    # a handful of SMs -- overlaps the next launch.  The timed region is still K whole steps.
-    n_streams = max(1, min(args.streams, 4))
-    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
-    cur = torch.cuda.current_stream(dev)
-
-    order = [None]  # --order profile: longest problems first, from the statistics of a previous solve
-
-    def run_steps(count):
-        outs = []
-        for s_ in streams:
-            s_.wait_stream(cur)
-        for i in range(count):
-            outs.append(eng.solve_batch(d_params, d_x0, settings, stream=streams[i % n_streams], order=order[0]))
-        for s_ in streams:
-            cur.wait_stream(s_)
-        return outs
-
-    warm = run_steps(args.warmup)
-    if args.order == "profile" and warm:
-        torch.cuda.synchronize()
-        order[0] = torch.argsort(warm[-1]["stats"][:, 2], descending=True).to(torch.int32)
-        run_steps(1)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(cur)
-    outs = run_steps(args.steps)
-    e1.record(cur)
-    barrier()
-    ms_local = e0.elapsed_time(e1)
-    ms_total = reduce_max(ms_local)
-    clocks = sampler.stop() if rank == 0 else None
-    out = outs[-1]
-    verdict = out["verdict"].cpu().numpy()
-    stats = out["stats"].cpu().numpy()
-    for o_ in outs[:-1]:
-        if not torch.equal(o_["verdict"], out["verdict"]) or not torch.equal(o_["x"], out["x"]):
-            raise SystemExit("bench.py: two steps over the same batch disagree")
-    converged = reduce_sum(float((verdict == 1).sum()))
-    value = converged * args.steps / (ms_total * 1e-3)
+    main = time_config(args, args.config, B, args.steps, args.warmup, dev, local, rank, world, dist,
+                       sampler_on=(rank == 0))
+    st, eng, host = main["st"], main["eng"], main["host"]
+    stats, verdict = host["stats"], host["verdict"]
+    ms_step = main["ms_total"] / args.steps
     # per-rank view of the tail: every rank's own device time and its longest problem (the step ends
     # when the rank that holds the longest problems is done)
-    per_rank = [[ms_local / args.steps, float(stats[:, 2].max()), float(stats[:, 2].astype(np.float64).sum())]]
+    per_rank = [[main["ms_local"] / args.steps, float(stats[:, 2].max()), float(stats[:, 2].astype(np.float64).sum())]]
     if world > 1:
         t = torch.tensor(per_rank[0], dtype=torch.float64, device=dev)
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
         per_rank = [a.cpu().tolist() for a in allt]
-
-    # ---- end-to-end leg: host buffers through the C ABI (sco_solve_batch_host_async), the H2D copy
-    # of every step's inputs and the D2H copy of its results inside the timed region, same pipelining
-    def host_out():
-        return dict(x=torch.empty((B, st.n), dtype=torch.float64, pin_memory=True).numpy(),
-                    verdict=torch.empty(B, dtype=torch.int32, pin_memory=True).numpy(),
-                    merit=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
-                    objective=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
-                    max_vio=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
-                    stats=torch.empty((B, 4), dtype=torch.int32, pin_memory=True).numpy())
-
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h_outs = [host_out() for _ in range(min(e2e_steps, n_streams))]
-
-    def run_e2e(count):
-        for i in range(count):
-            eng.solve_batch_host(h_params.numpy(), h_x0.numpy(), settings, out=h_outs[i % len(h_outs)],
-                                 stream=streams[i % n_streams])
-        for s_ in streams:
-            s_.synchronize()
-
-    run_e2e(1)  # warm-up (staging allocations)
-    barrier()
-    t0 = time.perf_counter()
-    run_e2e(e2e_steps)
-    barrier()
-    e2e_s = reduce_max(time.perf_counter() - t0)
-    h_out = h_outs[0]
-    e2e_conv = reduce_sum(float((h_out["verdict"] == 1).sum()))
-    e2e_value = e2e_conv * e2e_steps / e2e_s
-    h2d = h_params.numel() * 8 + h_x0.numel() * 8
-    d2h = sum(v.nbytes for v in h_out.values())
-    for ho in h_outs:
-        if not np.array_equal(ho["verdict"], verdict) or not np.array_equal(ho["x"], out["x"].cpu().numpy()):
-            raise SystemExit("bench.py: host-buffer path and device path disagree")
-
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (k_solve: one launch per step)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    ms_step = ms_total / args.steps
-    abytes, b_qp, b_cvx = algorithmic_bytes(st, stats)
-    achieved = abytes / (ms_step * 1e-3) / 1e9
-    flops, per_iter = admm_flops(st, stats)
     import ctypes
     tf = ctypes.c_double(0.0)
     _lib.check(eng.lib.sco_probe_fp64(local, ctypes.byref(tf)))
-    fp64_achieved = flops / (ms_step * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.config, {}).get("dram_bytes_per_problem")
-            if traffic is not None:
-                traffic = traffic * B
-        except Exception:
-            traffic = None
-    roofline = {
-        "kernel": "k_solve (fused convexify + penalty-QP assembly + ADMM + merit/trust-region, one launch per step)",
-        "regime": "resident: the whole QP working set lives in shared memory for the solve",
-        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "peak_source": peak_src, "traffic": traffic,
-        "algorithmic_bytes_per_launch": abytes, "bytes_per_qp": b_qp, "bytes_per_convexification": b_cvx,
-        "fp64": {"achieved": fp64_achieved, "peak": tf.value, "unit": "TFLOP/s",
-                 "frac": fp64_achieved / tf.value if tf.value else None, "flops_per_admm_iter": per_iter,
-                 "peak_source": "sco_probe_fp64 (DFMA loop, measured in this run)",
-                 "note": "the resident ADMM is bound by the FP64 pipe / shared memory, not HBM: its HBM "
-                         "fraction is small by construction (DESIGN.md section 4)"},
-    }
+    roofline = roofline_of(args.config, st, stats, ms_step, tf.value, B)
+    team, smem_bytes, occupancy = eng.team, eng.smem_bytes, eng.occupancy
+    eng.close()
 
-    # ---- CPU baseline (bounded sample, same workload, host cores of this box)
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        arm = CpuArm(args.config, args.cpu_cores)
-        count = args.cpu_sample or 2 * arm.cores
-        s = arm.sample(count)
-        arm.close()
-        cpu = {"value": s["converged"] / s["wall"], "unit": UNIT, "cores": arm.cores, "kind": "port",
-               "sample": "%d problems (indices 0..%d of the same workload), %.1f s wall; oracle port = reference "
-                         "algorithm bit-for-bit on the restated OSQP (upstream OSQP not installable here)"
-                         % (count, count - 1, s["wall"]),
-               "admm_iters_per_problem": s["admm_iters"] / count}
+    # ---- oracle audit + CPU baseline: one CPU pass over a random subsample of the batch (outside every timed region)
+    cpu, audit = None, None
+    if world == 1 and args.audit > 0 and not args.no_cpu_baseline:
+        idx = np.random.default_rng(12345).permutation(B)[:args.audit]
+        audit, cpu = audit_against_oracle(args.config, idx, host, args.audit_seconds, args.cpu_cores, first=rank * B)
 
+    # ---- the trajectory configurations (BASELINE.json configs[1], configs[2]) at their own batch sizes
+    others = {}
+    if world == 1 and not args.no_other_configs and args.config == "qcqp":
+        for name, Bo in (("point_robot", 1024), ("arm", 4096)):
+            try:
+                r = time_config(args, name, Bo, steps=2, warmup=1, dev=dev, local=local, rank=0, world=1, dist=dist,
+                                sampler_on=False, e2e=True)
+                h = r["host"]
+                ms_o = r["ms_total"] / 2
+                entry = {"config": workload_config(args, name, Bo), "value": r["value"], "unit": UNIT, "steps": 2, "warmup": 1,
+                         "ms_per_step": ms_o, "e2e": r["e2e"], "gpu_launches": 2,
+                         "roofline": roofline_of(name, r["st"], h["stats"], ms_o, tf.value, Bo),
+                         "converged": int((h["verdict"] == 1).sum()), "problems": Bo,
+                         "mean_admm_iters": float(h["stats"][:, 2].mean()), "max_admm_iters": int(h["stats"][:, 2].max()),
+                         "team": r["eng"].team, "smem_bytes": r["eng"].smem_bytes, "ctas_per_sm": r["eng"].occupancy}
+                r["eng"].close()
+                if args.audit > 0 and not args.no_cpu_baseline:
+                    idx = np.random.default_rng(12345).permutation(Bo)[:min(args.audit, 64)]
+                    entry["audit"], entry["cpu_baseline"] = audit_against_oracle(name, idx, h, args.other_audit_seconds,
+                                                                                 args.cpu_cores)
+                others[name] = entry
+            except Exception as ex:  # never lose the headline line to a side measurement
+                others[name] = {"error": repr(ex)}
+
+    busiest = max(range(len(per_rank)), key=lambda r: per_rank[r][0])
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, B),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+        "config": workload_config(args, args.config, B),
+        "clocks": main["clocks"],
+        "e2e": main["e2e"],
         "gpu_launches": args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "detail": {"converged": int(converged), "problems": B * world,
+        "detail": {"converged": int(main["converged"]), "problems": B * world,
                    "verdict_counts": {str(k): int((verdict == k).sum()) for k in (-1, 0, 1)},
                    "mean_sqp_iters": float(stats[:, 0].mean()), "mean_qp_solves": float(stats[:, 1].mean()),
                    "mean_admm_iters": float(stats[:, 2].mean()), "max_admm_iters": int(stats[:, 2].max()),
+                   "audit": audit,
                    "per_rank": [{"rank": r, "ms_per_step": round(v[0], 1), "max_admm_iters": int(v[1]),
                                  "busy_fraction": round(v[0] / ms_step, 3), "total_admm_iters": int(v[2])}
                                 for r, v in enumerate(per_rank)],
-                   "team": eng.team, "smem_bytes": eng.smem_bytes, "ctas_per_sm": eng.occupancy,
-                   "gen_seconds": t_gen},
+                   "limiter": "rank %d: a problem is sequential, its longest one needs %d ADMM iterations (k_solve tail); "
+                              "every rank holds the same total work within 2 %%" % (busiest, int(per_rank[busiest][1])),
+                   "team": team, "smem_bytes": smem_bytes, "ctas_per_sm": occupancy,
+                   "gen_seconds": main["t_gen"], "other_configs": others},
     }
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
@@ -453,14 +580,18 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="qcqp", choices=["qcqp", "point_robot", "arm"])
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (0 = as many as --steps)")
     ap.add_argument("--order", default="index", choices=["index", "profile"],
                     help="work-queue order: index (default) or profile = longest first by the ADMM iteration counts "
                          "of the last warm-up step (sco_solve_batch_ordered; for callers that re-solve similar batches)")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the steps are pipelined over (1..4)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU sample (default: two per core)")
+    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the steps are pipelined over (1..8)")
+    ap.add_argument("--audit", type=int, default=256, help="problems of the batch audited against the CPU oracle after "
+                                                            "the timed regions (0 = none); the same pass is the cpu_baseline")
+    ap.add_argument("--audit-seconds", type=float, default=60.0, help="wall-clock budget of the audit pass")
+    ap.add_argument("--other-audit-seconds", type=float, default=20.0)
     ap.add_argument("--cpu-cores", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU pass (audit and cpu_baseline)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip detail.other_configs (C2 / C3)")
     args = ap.parse_args()
     args.cpu_cores = args.cpu_cores or None
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -64,6 +64,7 @@ extern "C" {
 #define SCO_VERDICT_FAILED 0        /* solve() would return False                         */
 #define SCO_VERDICT_CONVERGED 1     /* solve() would return True                          */
 #define SCO_VERDICT_ITER_CAP (-1)   /* safety cap on SQP iterations hit (reference: none) */
+#define SCO_VERDICT_BAD_ORDER (-3)  /* sco_solve_batch_ordered: d_order is not a permutation of 0..B-1 */
 
 #define SCO_OK 0
 #define SCO_ERR_ARG (-1)
@@ -113,6 +114,16 @@ typedef struct {
   sco_field obj_prog;
   int32_t obj_prog_len; /* instructions; 0 = none */
   int32_t pad_;
+  /* AffExpr objective terms (prob.py:97-103 files them under _quad_obj_exprs): the sum of their A rows, n doubles
+   * (their constants go into c).  The exact merit uses a'x (AffExpr.eval, expr.py:173-174); the QP uses
+   * w * a'x with the weight of quirk C-4 (prob.py:220-221,240-249,424-426: every update_obj appends another
+   * copy and multiplies all copies by the penalty coefficient, w <- (w + 1) * mu) unless
+   * sco_settings.aff_obj_quirk = 0 (w = 1, the Gurobi backend's semantics). */
+  sco_field qa;
+  /* user bounds of the scalar variables (OSQPVar lb / ub), n doubles each; honoured by the closest-point QP
+   * (prob.py:369-412) -- the first trust region overwrites them (variable.py:37-45).  -1 = (-inf, +inf). */
+  sco_field lb0;
+  sco_field ub0;
 } sco_structure_desc;
 
 typedef struct {
@@ -147,6 +158,11 @@ typedef struct {
   int32_t duplicate_rows;   /* C-3, prob.py:508-509 */
   int32_t threads_per_problem; /* 0 = choose from the structure */
   int32_t force_generic;       /* 1 = never take the register-resident dense ADMM loop (A/B parity checks) */
+  int32_t aff_obj_quirk;       /* C-4, prob.py:240-249: AffExpr objectives weighted like penalty terms */
+  int32_t warm_start;          /* 0 = every QP starts from x = z = y = 0 like the reference (osqp_utils.py:195 builds a
+                                  new OSQP object per call); 1 = QPs inside one trust-region loop (only l, u change,
+                                  solver.py:136-146) reuse scaling and factorisation and start from the previous
+                                  iterates; 2 = additionally warm-start x, y across SQP iterations */
   int32_t pad_;
 } sco_settings;
 
@@ -175,15 +191,43 @@ int sco_solve_batch_ordered(sco_handle *h, int64_t B, const double *d_params, co
                             double *d_objective, double *d_max_vio, int32_t *d_stats, const int32_t *d_order,
                             void *stream);
 
-/* Launches of one handle may be in flight on several streams at once (each owns one of four launch
+/* The general form: every buffer of a batch in one struct (device pointers; NULL = not wanted / not given).
+ *   nonconverged[b]: bit g      <=> constraint group g (sorted group ids, prob.py:540-542) is in
+ *                                   prob.nonconverged_groups after the first loop of solver.py:209-225,
+ *                    bit 16 + g <=> group g is appended again by the second loop (solver.py:231-233);
+ *                    the value of the last evaluation of that block, like the attribute of the reference.
+ *   order: see sco_solve_batch_ordered.  An order that is not a permutation of 0..B-1 is detected on the
+ *          device before the solve starts; every verdict of the batch is then SCO_VERDICT_BAD_ORDER and nothing
+ *          else is written.
+ *   y_warm / x_warm: reserved (must be NULL). */
+typedef struct {
+  const double *d_params, *d_x0;
+  double *d_x_out;
+  int32_t *d_verdict;
+  double *d_merit, *d_objective, *d_max_vio;
+  int32_t *d_stats;
+  int32_t *d_nonconverged;
+  const int32_t *d_order;
+  const double *d_x_warm, *d_y_warm;
+} sco_batch_io;
+int sco_solve_batch_io(sco_handle *h, int64_t B, const sco_batch_io *io, const sco_settings *s, void *stream);
+
+/* Launches of one handle may be in flight on several streams at once (each owns one of SCO_LAUNCH_SLOTS launch
  * slots: work-queue counter + Jacobian scratch); calls on one handle must come from one host thread. */
+#define SCO_LAUNCH_SLOTS 16
+#define SCO_STAGING_SETS 8
 
 /* Same with HOST buffers: copies in, solves, copies out -- all enqueued on `stream`, no host
  * synchronisation (pinned buffers make the copies asynchronous; the caller synchronises the stream
- * before reading the outputs).  Up to four calls may be in flight (one staging set each). */
+ * before reading the outputs).  Up to SCO_STAGING_SETS calls may be in flight (one staging set each).
+ * `nonconverged` may be NULL (see sco_batch_io). */
 int sco_solve_batch_host_async(sco_handle *h, int64_t B, const double *params, const double *x0,
                                const sco_settings *s, double *x_out, int32_t *verdict, double *merit,
                                double *objective, double *max_vio, int32_t *stats, void *stream);
+int sco_solve_batch_host_groups(sco_handle *h, int64_t B, const double *params, const double *x0,
+                                const sco_settings *s, double *x_out, int32_t *verdict, double *merit,
+                                double *objective, double *max_vio, int32_t *stats, int32_t *nonconverged,
+                                void *stream);
 
 /* Same on the default stream, then synchronises (pinned or pageable buffers). */
 int sco_solve_batch_host(sco_handle *h, int64_t B, const double *params, const double *x0,
@@ -207,6 +251,12 @@ int sco_qp_solve(sco_handle *h, int64_t B, const double *d_params, const double 
                  const double *d_pi, const int32_t *d_kdup, const double *d_xref, int use_penalty,
                  int closest_point, const sco_settings *s, double *d_xq, int32_t *d_status,
                  int32_t *d_iters, void *stream);
+/* Same with the weight of the AffExpr objective terms per problem (d_wa[B]; NULL = 1, see sco_structure_desc.qa). */
+int sco_qp_solve_w(sco_handle *h, int64_t B, const double *d_params, const double *d_J,
+                   const double *d_b, const uint32_t *d_mask, const double *d_lbx, const double *d_ubx,
+                   const double *d_pi, const int32_t *d_kdup, const double *d_wa, const double *d_xref,
+                   int use_penalty, int closest_point, const sco_settings *s, double *d_xq, int32_t *d_status,
+                   int32_t *d_iters, void *stream);
 
 /* merit[B] = obj + mu*sum(viol), model[B] = obj + mu*sum(pen(Jx+b)) (J, b from a previous
  * sco_convexify at another point), max_vio[B], group sums gv[B,n_groups] / gm[B,n_groups]. */

@@ -41,11 +41,16 @@ def build_prob(ref, st, row, x0):
     prob = ref["prob"].Prob()
     ovars = np.empty((n, 1), dtype=object)
     for j in range(n):
-        ovars[j, 0] = ref["osqp_utils"].OSQPVar("x%05d" % j)  # sorts before "z+_pos_osqp_var"
+        if pp.lb0 is not None:
+            ovars[j, 0] = ref["osqp_utils"].OSQPVar("x%05d" % j, float(pp.lb0[j]), float(pp.ub0[j]))
+        else:
+            ovars[j, 0] = ref["osqp_utils"].OSQPVar("x%05d" % j)  # sorts before "z+_pos_osqp_var"
         prob.add_osqp_var(ovars[j, 0])
     var = ref["variable"].Variable(ovars, value=np.asarray(x0, dtype=float).reshape(n, 1))
     prob.add_var(var)
     prob.add_obj_expr(ex.BoundExpr(ex.QuadExpr(pp.Q, pp.q.reshape(1, n), np.array([[pp.c]])), var))
+    if pp.qa is not None:  # AffExpr objective term (quirk C-4)
+        prob.add_obj_expr(ex.BoundExpr(ex.AffExpr(pp.qa.reshape(1, n), np.zeros((1, 1))), var))
     if pp.obj_prog is not None:  # black-box objective term, as tests/sco_osqp/test_solver.py:66-68 adds it
         import families as fam
         prob.add_obj_expr(ex.BoundExpr(ex.Expr(lambda x: fam.vm_f(x, pp.obj_prog, 1)), var))
@@ -91,4 +96,4 @@ def solve_with_reference(ref, st, row, x0, solver=None, osqp_kw=None):
     x = var.get_value()[:, 0]
     mu_final = None
     return dict(x=x.copy(), success=bool(ok), max_vio=float(prob.get_max_cnt_violation()),
-                prob=prob, var=var)
+                prob=prob, var=var, nonconverged=list(prob.nonconverged_groups))

@@ -108,6 +108,13 @@ class PortProblem(object):
         self.Q = _field(st, st.Q, row, n * n).reshape(n, n)
         self.q = _field(st, st.q, row, n)
         self.c = float(_field(st, st.c, row, 1)[0])
+        # AffExpr objective terms (prob.py:97-103 files them under _quad_obj_exprs): exact value qa'x, QP weight `wa`
+        self.qa = _field(st, st.qa, row, n) if getattr(st, "qa", None) is not None and st.qa.off >= 0 else None
+        self.wa = 0.0
+        self.lb0 = self.ub0 = None  # user bounds of the scalar variables (OSQPVar lb / ub)
+        if getattr(st, "lb0", None) is not None and st.lb0.off >= 0:
+            self.lb0, self.ub0 = _field(st, st.lb0, row, n), _field(st, st.ub0, row, n)
+        self.nonconverged = []  # prob.nonconverged_groups (group indices, reference order incl. its duplicates)
         self.m_lin = st.m_lin
         if st.m_lin:
             self.A_lin = sp.csr_matrix((st.lin_val, st.lin_col, st.lin_rowptr), shape=(st.m_lin, n))
@@ -139,6 +146,8 @@ class PortProblem(object):
     def objective(self, x):
         # QuadExpr.eval, expr.py:205-206 (+ Expr.eval of the non-quadratic term, prob.py:573-574)
         v = float(0.5 * x[:, 0] @ (self.Q @ x[:, 0]) + self.q @ x[:, 0] + self.c)
+        if self.qa is not None:  # AffExpr.eval, expr.py:173-174
+            v += float(self.qa @ x[:, 0])
         if self.obj_prog is not None:
             v += float(fam.vm_f(x, self.obj_prog, 1)[0, 0])
         return v
@@ -146,6 +155,8 @@ class PortProblem(object):
     def objective_model(self, x):
         # quadratic terms + the degree-2 model of the non-quadratic one (prob.py:624-626)
         v = float(0.5 * x[:, 0] @ (self.Q @ x[:, 0]) + self.q @ x[:, 0] + self.c)
+        if self.qa is not None:
+            v += float(self.qa @ x[:, 0])
         if self.obj_prog is not None:
             v += float(0.5 * x[:, 0] @ (self.Hq @ x[:, 0]) + self.aq @ x[:, 0] + self.bq)
         return v
@@ -217,6 +228,9 @@ class PortProblem(object):
             self.masks = [np.ones_like(J, dtype=bool) for J in self.J]
         self.kdup = self.kdup + 1 if q.get("duplicate_rows", True) else 1
         self.pi = self.pi * mu if q.get("compound_penalty", True) else mu
+        # quirk C-4 (prob.py:220-221,240-249 then 424-426): another copy of the AffExpr objective coefficients is
+        # appended to the penalty terms, then every stored coefficient is multiplied by the penalty coefficient
+        self.wa = (self.wa + 1.0) * mu if q.get("aff_obj_quirk", True) else 1.0
 
     # -- QP ------------------------------------------------------------------
     def solve_qp(self, lbx, ubx, penalty, osqp_kw, P_override=None, q_override=None):
@@ -232,6 +246,8 @@ class PortProblem(object):
         else:
             P[:n, :n] = 0.5 * (self.Q + self.Q.T)
             qv[:n] = self.q
+            if self.qa is not None:
+                qv[:n] += self.wa * self.qa
             if self.obj_prog is not None and self.Hq is not None:  # prob.py:348-367
                 P[:n, :n] += 0.5 * (self.Hq + self.Hq.T)
                 qv[:n] += self.aq
@@ -292,7 +308,8 @@ class PortProblem(object):
         n = self.n
         x0 = self.x[:, 0]
         inf = np.full(n, np.inf)
-        return self.solve_qp(-inf, inf, False, DEFAULT_OSQP, P_override=2.0 * np.eye(n),
+        lo, hi = (-inf, inf) if self.lb0 is None else (self.lb0, self.ub0)  # whatever is on the OSQPVars
+        return self.solve_qp(lo, hi, False, DEFAULT_OSQP, P_override=2.0 * np.eye(n),
                              q_override=-2.0 * x0)
 
 
@@ -312,7 +329,7 @@ def solve(st, row, x0, solver=None, osqp_kw=None, max_sqp_iters=10000, keep_trac
     def result(ok):
         return dict(x=p.x[:, 0].copy(), success=bool(ok), merit=p.get_value(mu),
                     objective=p.objective(p.x), max_vio=p.get_max_cnt_violation(),
-                    stats=dict(p.stats), trace=p.trace, mu=mu)
+                    stats=dict(p.stats), trace=p.trace, mu=mu, nonconverged=list(p.nonconverged))
 
     if not p.find_closest_feasible_point():  # solver.py:81-82
         return result(False)
@@ -375,8 +392,12 @@ def _min_merit_fn(p, S, O, mu, delta, max_sqp_iters, keep_trace):  # solver.py:1
                                 break
                     if not ov:
                         nonconv.append(g)
+            p.nonconverged = list(nonconv)  # solver.py:208: cleared at every evaluation of this block
             if nonconv:
                 p.x = p.x_saved.copy()
+                for g in range(ng):  # solver.py:231-233: appended again, without the overlap rule
+                    if violated[g] and approx_vec[g] < S["min_approx_improve"]:
+                        p.nonconverged.append(g)
                 return True
             if exact < 0 or ratio < S["improve_ratio_threshold"]:  # _shrink_trust_region
                 p.x = p.x_saved.copy()

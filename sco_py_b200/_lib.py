@@ -30,7 +30,14 @@ class CStructure(ctypes.Structure):
                 ("Q", CField), ("q", CField), ("c", CField), ("lin_l", CField), ("lin_u", CField),
                 ("lin_rowptr", c_vp), ("lin_col", c_vp), ("lin_val", c_vp), ("shared", c_vp),
                 ("group_overlap", c_vp), ("blocks", CBlock * MAX_BLOCKS),
-                ("obj_prog", CField), ("obj_prog_len", c_i32), ("pad_", c_i32)]
+                ("obj_prog", CField), ("obj_prog_len", c_i32), ("pad_", c_i32),
+                ("qa", CField), ("lb0", CField), ("ub0", CField)]
+
+
+class CBatchIO(ctypes.Structure):
+    _fields_ = [("d_params", c_vp), ("d_x0", c_vp), ("d_x_out", c_vp), ("d_verdict", c_vp), ("d_merit", c_vp),
+                ("d_objective", c_vp), ("d_max_vio", c_vp), ("d_stats", c_vp), ("d_nonconverged", c_vp),
+                ("d_order", c_vp), ("d_x_warm", c_vp), ("d_y_warm", c_vp)]
 
 
 class CSettings(ctypes.Structure):
@@ -45,13 +52,15 @@ class CSettings(ctypes.Structure):
         ("osqp_max_iter", c_i32), ("osqp_scaling", c_i32), ("osqp_check_termination", c_i32),
         ("osqp_adaptive_rho", c_i32), ("osqp_adaptive_rho_interval", c_i32),
         ("compound_penalty", c_i32), ("freeze_sparsity", c_i32), ("duplicate_rows", c_i32),
-        ("threads_per_problem", c_i32), ("force_generic", c_i32), ("pad_", c_i32),
+        ("threads_per_problem", c_i32), ("force_generic", c_i32), ("aff_obj_quirk", c_i32),
+        ("warm_start", c_i32), ("pad_", c_i32),
     ]
 
 
 EXPORTS = ["sco_last_error", "sco_default_settings", "sco_create", "sco_destroy", "sco_query",
-           "sco_solve_batch", "sco_solve_batch_ordered", "sco_solve_batch_host", "sco_solve_batch_host_async", "sco_convexify", "sco_qp_solve", "sco_merit",
-           "sco_probe_fp64"]
+           "sco_solve_batch", "sco_solve_batch_ordered", "sco_solve_batch_io", "sco_solve_batch_host",
+           "sco_solve_batch_host_async", "sco_solve_batch_host_groups", "sco_convexify", "sco_qp_solve",
+           "sco_qp_solve_w", "sco_merit", "sco_probe_fp64"]
 
 _lib = None
 
@@ -77,6 +86,12 @@ def load():
                                     c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.sco_solve_batch_ordered.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(CSettings), c_vp, c_vp,
                                             c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.sco_solve_batch_io.argtypes = [c_vp, c_i64, ctypes.POINTER(CBatchIO), ctypes.POINTER(CSettings), c_vp]
+    lib.sco_solve_batch_host_groups.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(CSettings), c_vp,
+                                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.sco_qp_solve_w.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                   ctypes.c_int, ctypes.c_int, ctypes.POINTER(CSettings), c_vp, c_vp,
+                                   c_vp, c_vp]
     lib.sco_solve_batch_host.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(CSettings), c_vp,
                                          c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.sco_solve_batch_host_async.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(CSettings), c_vp,

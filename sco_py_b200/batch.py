@@ -25,6 +25,8 @@ class Compiled(object):
         self.slots = []          # (Variable, flat index inside it, global column)
         self.x0 = None
         self.Q = self.q = None
+        self.qa = None           # summed A rows of AffExpr objective terms (quirk C-4)
+        self.lb0 = self.ub0 = None  # user bounds of the scalar variables
         self.c = 0.0
         self.lin_A = self.lin_l = self.lin_u = None
         self.blocks = []         # (family expr, cnt_type, val[m], group ids)
@@ -60,6 +62,10 @@ def compile_problem(prob):
     if np.isnan(x0).any():
         raise UnsupportedProblem("every variable needs an initial value (Variable(osqp_vars, value))")
     cp.x0 = x0
+    lb = np.array([float(ov.get_lower_bound()) for ov in cp.ovars])
+    ub = np.array([float(ov.get_upper_bound()) for ov in cp.ovars])
+    if np.isfinite(lb).any() or np.isfinite(ub).any():
+        cp.lb0, cp.ub0 = lb, ub
     # ---- objective: QuadExpr terms summed (prob.py:97-103, 348-367)
     cp.Q = np.zeros((n, n))
     cp.q = np.zeros(n)
@@ -71,10 +77,15 @@ def compile_problem(prob):
             cp.q[cols] += np.asarray(e.A).ravel()
             cp.c += float(np.asarray(e.b).ravel()[0])
         else:
-            raise UnsupportedProblem(
-                "AffExpr objectives: the OSQP backend of the reference turns them into penalty terms scaled by "
-                "the penalty coefficient (prob.py:220-221,240-249; SURVEY.md quirk C-4).  Fold the linear term "
-                "into QuadExpr.A instead.")
+            # AffExpr objective: exact value a'x + b in the merits (expr.py:173-174); in the QP the reference's OSQP
+            # backend files the coefficients under the PENALTY terms, re-appended and re-scaled by the penalty
+            # coefficient at every update_obj (prob.py:220-221,240-249,424-426) -- kept
+            # apart here so the device can apply that weight (or weight 1 with sco_settings.aff_obj_quirk = 0)
+            A = np.asarray(e.A, dtype=float)
+            if cp.qa is None:
+                cp.qa = np.zeros(n)
+            np.add.at(cp.qa, cols, A.sum(axis=0))  # eval() sums the rows (prob.py:573-574)
+            cp.c += float(np.asarray(e.b, dtype=float).sum())
     if prob._nonquad_obj_exprs:  # convexified to degree 2 on the device (expr.py:143-153)
         if len(prob._nonquad_obj_exprs) > 1:
             raise UnsupportedProblem("more than one non-quadratic objective term: add them up in one SymExpr")
@@ -87,6 +98,8 @@ def compile_problem(prob):
                                      "cannot run on the device and there is no CPU fallback")
         if n > 16:
             raise UnsupportedProblem("non-quadratic objectives are limited to 16 variables (serial eigenvalue shift)")
+        if b.expr.n != n:
+            raise UnsupportedProblem("the objective SymExpr is over %d variables, the problem has %d" % (b.expr.n, n))
         cp.obj_prog = b.expr
     # ---- linear constraints
     rows_A, rows_l, rows_u = [], [], []
@@ -116,6 +129,11 @@ def compile_problem(prob):
         if cols.size != n or not np.array_equal(cols, np.arange(n)):
             raise UnsupportedProblem("family constraints must be bound to a Variable that holds ALL scalar "
                                      "variables of the problem in QP order")
+        if getattr(fam, "n", n) != n:
+            raise UnsupportedProblem("a %s over %d variables is bound to a problem of %d variables"
+                                     % (type(fam).__name__, fam.n, n))
+        if isinstance(fam, E.CircleDistExpr) and 2 * fam.T > n:
+            raise UnsupportedProblem("CircleDistExpr: %d way-points need %d variables, the problem has %d" % (fam.T, 2 * fam.T, n))
         ctype = CNT_EQ if isinstance(comp, E.EqExpr) else CNT_LEQ
         val = np.asarray(comp.val, dtype=float).ravel()
         if val.size != fam.m:
@@ -139,7 +157,8 @@ def _csr(A):
 
 def group_key(cp):
     """What two compiled problems must have in common to go into one launch."""
-    return (cp.x0.size, None if cp.lin_A is None else (cp.lin_A.shape, cp.lin_A.tobytes()), tuple(cp.gids),
+    return (cp.x0.size, cp.qa is not None, cp.lb0 is not None,
+            None if cp.lin_A is None else (cp.lin_A.shape, cp.lin_A.tobytes()), tuple(cp.gids),
             tuple((b[0].family, b[0].m, b[1], tuple(b[0].ipar), tuple(b[3])) for b in cp.blocks),
             None if cp.obj_prog is None else cp.obj_prog.n_instr)
 
@@ -157,7 +176,8 @@ def compile_batch(probs, compiled=None):
                 (c.lin_A is None or (c.lin_A.shape == c0.lin_A.shape and np.array_equal(c.lin_A, c0.lin_A))) and
                 all(a[0].family == b[0].family and a[0].m == b[0].m and a[1] == b[1] and a[3] == b[3] and
                     list(a[0].ipar) == list(b[0].ipar) for a, b in zip(c.blocks, c0.blocks)) and
-                (c.obj_prog is None) == (c0.obj_prog is None) and
+                (c.obj_prog is None) == (c0.obj_prog is None) and (c.qa is None) == (c0.qa is None) and
+                (c.lb0 is None) == (c0.lb0 is None) and
                 (c.obj_prog is None or c.obj_prog.n_instr == c0.obj_prog.n_instr))
         if not same:
             raise UnsupportedProblem("problem %d of the batch does not share the structure of problem 0" % i)
@@ -192,13 +212,22 @@ def compile_batch(probs, compiled=None):
     cf = own_field(1)
     fills.append((cf, lambda c: np.array([c.c])))
     kw = {}
+    if c0.qa is not None:
+        qaf = own_field(n)
+        fills.append((qaf, lambda c: c.qa))
+        kw["qa"] = qaf
+    if c0.lb0 is not None:
+        lf0, uf0 = own_field(n), own_field(n)
+        fills.append((lf0, lambda c: c.lb0))
+        fills.append((uf0, lambda c: c.ub0))
+        kw.update(lb0=lf0, ub0=uf0)
     if c0.lin_A is not None:
         m_lin = c0.lin_A.shape[0]
         rp, ci, cv = _csr(c0.lin_A)
         lf, uf = own_field(m_lin), own_field(m_lin)
         fills.append((lf, lambda c: c.lin_l))
         fills.append((uf, lambda c: c.lin_u))
-        kw = dict(m_lin=m_lin, lin_rowptr=rp, lin_col=ci, lin_val=cv, lin_l=lf, lin_u=uf)
+        kw.update(m_lin=m_lin, lin_rowptr=rp, lin_col=ci, lin_val=cv, lin_l=lf, lin_u=uf)
     if c0.obj_prog is not None:
         p0 = c0.obj_prog.params()
         if B > 1 and all(np.array_equal(c.obj_prog.params(), p0) for c in cps[1:]):
@@ -220,8 +249,10 @@ def compile_batch(probs, compiled=None):
         mask = 0
         for g in gids:
             mask |= 1 << c0.gids.index(g)
-        blocks.append(Block(fam.family, ctype, fam.m, pf, vf, ipar=list(fam.ipar), group_mask=mask or 1, jw=fam.jw))
-    ng = max(1, len(c0.gids))
+        # group_ids=[] puts a constraint in NO group (prob.py:135-142): mask 0, and a problem without any group
+        # has n_groups = 0 -- the reference then skips the per-group test (solver.py:209)
+        blocks.append(Block(fam.family, ctype, fam.m, pf, vf, ipar=list(fam.ipar), group_mask=mask, jw=fam.jw))
+    ng = len(c0.gids)
     overlap = np.zeros((ng, ng), dtype=np.int32)
     ov = getattr(probs[0], "_cnt_groups_overlap", {}) if probs else {}
     for g, others in ov.items():
@@ -248,7 +279,8 @@ def signature(st):
     lin = None
     if st.m_lin:
         lin = (st.lin_rowptr.tobytes(), st.lin_col.tobytes(), st.lin_val.tobytes(), fld(st.lin_l), fld(st.lin_u))
-    return (st.n, st.stride, fld(st.Q), fld(st.q), fld(st.c), fld(st.obj_prog), st.obj_prog_len, st.m_lin, lin, st.n_groups,
+    return (st.n, st.stride, fld(st.Q), fld(st.q), fld(st.c), fld(st.qa), fld(st.lb0), fld(st.ub0), fld(st.obj_prog),
+            st.obj_prog_len, st.m_lin, lin, st.n_groups,
             None if st.group_overlap is None else st.group_overlap.tobytes(),
             None if st.shared is None else st.shared.tobytes(),
             tuple((b.family, b.cnt_type, b.m, fld(b.par), fld(b.val), tuple(b.ipar), b.group_mask, b.jw)

@@ -37,6 +37,7 @@ struct sco_handle {
   int team = 32;
   const TeamOps *ops = nullptr;    // solve / qp (dense variant when the structure qualifies)
   const TeamOps *gen_ops = nullptr; // convexify / merit (generic team kernels)
+  int carve_ops = 100, carve_gen = 100;  // shared-memory carve-out of this handle (kernel attributes are shared)
   int sm_count = 0;
   int occupancy = 1;
   size_t smem_bytes = 0;
@@ -45,19 +46,23 @@ struct sco_handle {
   // Launch slots: every launch owns a work-queue counter and a Jacobian scratch area until it ends,
   // so launches of one handle may be in flight on several streams at once (batches pipelined over
   // streams hide the tail of a launch, where a few long problems keep a handful of SMs busy).
-  static const int NSLOT = 4;
-  double *Jscr[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+  static const int NSLOT = SCO_LAUNCH_SLOTS;
+  double *Jscr[NSLOT] = {};
   size_t Jscr_ctas = 0;
   unsigned long long *counter = nullptr;  // NSLOT counters
-  cudaEvent_t slot_done[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+  int *order_err = nullptr;               // NSLOT flags (sco_solve_batch_ordered)
+  unsigned *seen[NSLOT] = {};             // bitmap of the order check, grow-only
+  long long seen_cap[NSLOT] = {};
+  cudaEvent_t slot_done[NSLOT] = {};
   unsigned next_slot = 0;
-  // host-entry staging buffers, one set per slot (grow-only)
+  // host-entry staging buffers, one set per staging slot (grow-only)
+  static const int NSTG = SCO_STAGING_SETS;
   struct Staging {
     double *params = nullptr, *x0 = nullptr, *x = nullptr, *merit = nullptr, *obj = nullptr, *vio = nullptr;
-    int *verdict = nullptr, *stats = nullptr;
+    int *verdict = nullptr, *stats = nullptr, *nonconv = nullptr;
     long long cap_B = 0;
     cudaEvent_t done = nullptr;
-  } stg[NSLOT];
+  } stg[NSTG];
   unsigned next_stg = 0;
 };
 
@@ -140,6 +145,8 @@ extern "C" void sco_default_settings(sco_settings *s) {
   s->duplicate_rows = 1;
   s->threads_per_problem = 0;
   s->force_generic = 0;
+  s->aff_obj_quirk = 1;
+  s->warm_start = 0;
 }
 
 static DevSettings to_dev(const sco_settings *s) {
@@ -171,18 +178,51 @@ static DevSettings to_dev(const sco_settings *s) {
   d.freeze_sparsity = s->freeze_sparsity;
   d.duplicate_rows = s->duplicate_rows;
   d.force_generic = s->force_generic;
+  d.aff_obj_quirk = s->aff_obj_quirk;
+  d.warm_start = s->warm_start;
   return d;
 }
 
 extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle **out) {
   if (!desc || !out) return fail(SCO_ERR_ARG, "null argument");
-  if (desc->n <= 0 || desc->n_blocks < 0 || desc->n_blocks > SCO_MAX_BLOCKS)
-    return fail(SCO_ERR_ARG, "bad n / n_blocks");
-  if (desc->n_groups < 1 || desc->n_groups > SCO_MAX_GROUPS) return fail(SCO_ERR_ARG, "bad n_groups");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(SCO_ERR_CUDA, "no CUDA device: the engine has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(SCO_ERR_ARG, "device %d out of range", device);
+  if (desc->n <= 0 || desc->n_blocks < 0 || desc->n_blocks > SCO_MAX_BLOCKS)
+    return fail(SCO_ERR_ARG, "bad n / n_blocks");
+  // n_groups = 0: no constraint belongs to a group -- the reference then skips the per-group test (solver.py:209)
+  if (desc->n_groups < 0 || desc->n_groups > SCO_MAX_GROUPS) return fail(SCO_ERR_ARG, "bad n_groups");
+  if (desc->m_lin < 0 || desc->stride <= 0 || desc->shared_len < 0) return fail(SCO_ERR_ARG, "negative m_lin / stride / shared_len");
+  if (desc->shared_len > 0 && !desc->shared) return fail(SCO_ERR_ARG, "shared_len > 0 but shared is null");
+  {
+    // every field must lie inside the block it lives in (out-of-range offsets would be device reads out of bounds)
+    const long long n_ = desc->n;
+    auto field_ok = [&](const sco_field &f, long long len) {
+      if (f.off < 0) return true;
+      const long long lim = f.shared ? (long long)desc->shared_len : (long long)desc->stride;
+      return f.off + len <= lim;
+    };
+    bool okf = field_ok(desc->Q, n_ * n_) && field_ok(desc->q, n_) && field_ok(desc->c, 1) &&
+               field_ok(desc->lin_l, desc->m_lin) && field_ok(desc->lin_u, desc->m_lin) && field_ok(desc->qa, n_) &&
+               field_ok(desc->lb0, n_) && field_ok(desc->ub0, n_) &&
+               (desc->obj_prog_len <= 0 || field_ok(desc->obj_prog, 1 + 2LL * desc->obj_prog_len));
+    for (int bi = 0; bi < desc->n_blocks && okf; bi++) {
+      const sco_block_desc &b = desc->blocks[bi];
+      if (b.m <= 0) return fail(SCO_ERR_ARG, "block %d: m must be positive", bi);
+      if (desc->n_groups < 32 && (b.group_mask >> desc->n_groups) != 0)
+        return fail(SCO_ERR_ARG, "block %d: group_mask names a group >= n_groups", bi);
+      long long plen = 0;
+      if (b.family == SCO_FAM_QUADFORM) plen = (long long)b.m * (n_ * (n_ + 1) / 2 + n_);
+      else if (b.family == SCO_FAM_CIRCLE2D) plen = 3LL * b.ipar[1];
+      else if (b.family == SCO_FAM_FK7) plen = 30;
+      else if (b.family == SCO_FAM_VM) plen = b.m + 2LL * b.ipar[2];
+      if (b.par.off < 0) return fail(SCO_ERR_ARG, "block %d: parameters are missing", bi);
+      okf = field_ok(b.par, plen) && field_ok(b.val, b.m);
+    }
+    if (!okf) return fail(SCO_ERR_ARG, "a field lies outside its parameter block (offset + length > stride / shared_len)");
+    if (desc->m_lin > 0 && (desc->lin_l.off < 0 || desc->lin_u.off < 0)) return fail(SCO_ERR_ARG, "m_lin > 0 needs lin_l and lin_u");
+  }
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -201,6 +241,7 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   S.stride = desc->stride;
   S.Q = cvt(desc->Q); S.q = cvt(desc->q); S.c = cvt(desc->c);
   S.lin_l = cvt(desc->lin_l); S.lin_u = cvt(desc->lin_u);
+  S.qa = cvt(desc->qa); S.lb0 = cvt(desc->lb0); S.ub0 = cvt(desc->ub0);
   S.objp = cvt(desc->obj_prog); S.obj_len = desc->obj_prog_len > 0 && desc->obj_prog.off >= 0 ? desc->obj_prog_len : 0;
   if (S.obj_len && n > 16) { delete h; return fail(SCO_ERR_UNSUPPORTED, "non-quadratic objectives are limited to 16 variables"); }
   for (int g = 0; g < desc->n_groups; g++) {
@@ -328,8 +369,9 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
     h->ops = S.dense_kind == 1 ? sco_dense_ops_1() : S.dense_kind == 2 ? sco_dense_ops_2() : S.dense_kind == 3 ? sco_dense_ops_3() : sco_dense_ops_4();
   {
     int occ = 0;
-    cudaError_t ce = h->gen_ops->configure(h->smem_bytes, &occ);
-    if (ce == cudaSuccess && h->ops != h->gen_ops) ce = h->ops->configure(h->smem_bytes, &occ);
+    cudaError_t ce = h->gen_ops->configure(h->smem_bytes, &occ, &h->carve_gen);
+    h->carve_ops = h->carve_gen;
+    if (ce == cudaSuccess && h->ops != h->gen_ops) ce = h->ops->configure(h->smem_bytes, &occ, &h->carve_ops);
     if (ce != cudaSuccess) {
       sco_destroy(h);
       return fail(SCO_ERR_CUDA, "kernel configuration failed: %s", cudaGetErrorString(ce));
@@ -337,12 +379,13 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
     h->occupancy = std::max(occ, 1);
   }
   h->Jscr_ctas = (size_t)h->sm_count * h->occupancy;
-  bool ok = cudaMalloc(&h->counter, sco_handle::NSLOT * sizeof(unsigned long long)) == cudaSuccess;
-  for (int k = 0; k < sco_handle::NSLOT && ok; k++) {
+  bool ok = cudaMalloc(&h->counter, sco_handle::NSLOT * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc(&h->order_err, sco_handle::NSLOT * sizeof(int)) == cudaSuccess;
+  for (int k = 0; k < sco_handle::NSLOT && ok; k++)
     ok = cudaMalloc(&h->Jscr[k], std::max<size_t>(h->Jscr_ctas * std::max(jnnz, 1), 1) * sizeof(double)) == cudaSuccess &&
-         cudaEventCreateWithFlags(&h->slot_done[k], cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&h->stg[k].done, cudaEventDisableTiming) == cudaSuccess;
-  }
+         cudaEventCreateWithFlags(&h->slot_done[k], cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < sco_handle::NSTG && ok; k++)
+    ok = cudaEventCreateWithFlags(&h->stg[k].done, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     sco_destroy(h);
     return fail(SCO_ERR_CUDA, "cudaMalloc of scratch failed");
@@ -356,12 +399,16 @@ extern "C" int sco_destroy(sco_handle *h) {
   cudaSetDevice(h->device);
   for (void *p : h->dev_allocs) cudaFree(p);
   cudaFree(h->counter);
+  cudaFree(h->order_err);
   for (int k = 0; k < sco_handle::NSLOT; k++) {
     cudaFree(h->Jscr[k]);
+    cudaFree(h->seen[k]);
     if (h->slot_done[k]) cudaEventDestroy(h->slot_done[k]);
+  }
+  for (int k = 0; k < sco_handle::NSTG; k++) {
     sco_handle::Staging &g = h->stg[k];
     cudaFree(g.params); cudaFree(g.x0); cudaFree(g.x); cudaFree(g.merit); cudaFree(g.obj); cudaFree(g.vio);
-    cudaFree(g.verdict); cudaFree(g.stats);
+    cudaFree(g.verdict); cudaFree(g.stats); cudaFree(g.nonconv);
     if (g.done) cudaEventDestroy(g.done);
   }
   delete h;
@@ -373,6 +420,17 @@ extern "C" int sco_query(sco_handle *h, int64_t *out8) {
   out8[0] = h->S.n; out8[1] = h->S.m_nl; out8[2] = h->S.n_slack; out8[3] = h->S.jnnz;
   out8[4] = h->S.n_q; out8[5] = (int64_t)h->smem_bytes; out8[6] = h->team; out8[7] = h->occupancy;
   return SCO_OK;
+}
+
+// d_order must be a permutation of 0..B-1: every entry in range and seen once.  Violations are counted in *err;
+// k_solve reads it and refuses the batch (verdict -3 everywhere) -- stream-ordered, no host synchronisation.
+__global__ void k_check_order(const int *__restrict__ order, long long B, unsigned *seen, int *err) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x) {
+    const int v = order[i];
+    if (v < 0 || v >= B) { atomicAdd(err, 1); continue; }
+    const unsigned bit = 1u << (v & 31);
+    if (atomicOr(seen + (v >> 5), bit) & bit) atomicAdd(err, 1);
+  }
 }
 
 extern "C" int sco_solve_batch(sco_handle *h, int64_t B, const double *d_params, const double *d_x0,
@@ -387,18 +445,47 @@ extern "C" int sco_solve_batch_ordered(sco_handle *h, int64_t B, const double *d
                                        const sco_settings *s, double *d_x_out, int32_t *d_verdict,
                                        double *d_merit, double *d_objective, double *d_max_vio,
                                        int32_t *d_stats, const int32_t *d_order, void *stream) {
-  if (!h || !s) return fail(SCO_ERR_ARG, "null argument");
+  sco_batch_io io;
+  memset(&io, 0, sizeof(io));
+  io.d_params = d_params; io.d_x0 = d_x0; io.d_x_out = d_x_out; io.d_verdict = d_verdict; io.d_merit = d_merit;
+  io.d_objective = d_objective; io.d_max_vio = d_max_vio; io.d_stats = d_stats; io.d_order = d_order;
+  return sco_solve_batch_io(h, B, &io, s, stream);
+}
+
+extern "C" int sco_solve_batch_io(sco_handle *h, int64_t B, const sco_batch_io *io, const sco_settings *s, void *stream) {
+  if (!h || !s || !io) return fail(SCO_ERR_ARG, "null argument");
   if (B <= 0) return SCO_OK;  // an empty batch is valid and touches nothing
-  if (!d_params || !d_x0 || !d_x_out || !d_verdict) return fail(SCO_ERR_ARG, "null argument");
+  if (!io->d_params || !io->d_x0 || !io->d_x_out || !io->d_verdict) return fail(SCO_ERR_ARG, "null argument");
+  if (io->d_x_warm || io->d_y_warm) return fail(SCO_ERR_UNSUPPORTED, "x_warm / y_warm are reserved");
+  if (B > 0x7fffffffLL) return fail(SCO_ERR_ARG, "batch too large");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   DevSettings d = to_dev(s);
   const int slot = (int)(h->next_slot++ % sco_handle::NSLOT);
   CUDA_TRY(cudaStreamWaitEvent(st, h->slot_done[slot], 0));  // the slot's previous launch (any stream)
   CUDA_TRY(cudaMemsetAsync(h->counter + slot, 0, sizeof(unsigned long long), st));
+  const int *order_err = nullptr;
+  if (io->d_order) {
+    const long long words = (B + 31) / 32;
+    if (words > h->seen_cap[slot]) {
+      CUDA_TRY(cudaEventSynchronize(h->slot_done[slot]));
+      if (h->seen[slot]) cudaFree(h->seen[slot]);
+      h->seen[slot] = nullptr;
+      h->seen_cap[slot] = 0;
+      CUDA_TRY(cudaMalloc(&h->seen[slot], (size_t)words * sizeof(unsigned)));
+      h->seen_cap[slot] = words;
+    }
+    CUDA_TRY(cudaMemsetAsync(h->seen[slot], 0, (size_t)words * sizeof(unsigned), st));
+    CUDA_TRY(cudaMemsetAsync(h->order_err + slot, 0, sizeof(int), st));
+    const int blocks = (int)std::min<long long>((B + 255) / 256, 4096);
+    k_check_order<<<blocks, 256, 0, st>>>(io->d_order, (long long)B, h->seen[slot], h->order_err + slot);
+    CUDA_TRY(cudaGetLastError());
+    order_err = h->order_err + slot;
+  }
   const long long grid = std::min<long long>(B, (long long)h->Jscr_ctas);
-  SolveArgs a = {(long long)B, d_params, d_x0, d_x_out, d_verdict, d_merit, d_objective, d_max_vio, d_stats,
-                 h->Jscr[slot], h->counter + slot, d_order};
+  SolveArgs a = {(long long)B, io->d_params, io->d_x0, io->d_x_out, io->d_verdict, io->d_merit, io->d_objective,
+                 io->d_max_vio, io->d_stats, h->Jscr[slot], h->counter + slot, io->d_order, io->d_nonconverged, order_err};
+  CUDA_TRY(h->ops->prepare(h->carve_ops));
   h->ops->solve((unsigned)grid, h->smem_bytes, st, h->S, d, a);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(h->slot_done[slot], st));
@@ -417,26 +504,39 @@ extern "C" int sco_solve_batch_host_async(sco_handle *h, int64_t B, const double
                                           const sco_settings *s, double *x_out, int32_t *verdict,
                                           double *merit, double *objective, double *max_vio,
                                           int32_t *stats, void *stream) {
+  return sco_solve_batch_host_groups(h, B, params, x0, s, x_out, verdict, merit, objective, max_vio, stats, nullptr,
+                                     stream);
+}
+
+extern "C" int sco_solve_batch_host_groups(sco_handle *h, int64_t B, const double *params, const double *x0,
+                                           const sco_settings *s, double *x_out, int32_t *verdict,
+                                           double *merit, double *objective, double *max_vio,
+                                           int32_t *stats, int32_t *nonconverged, void *stream) {
   if (!h || !s) return fail(SCO_ERR_ARG, "null argument");
   if (B <= 0) return SCO_OK;
   if (!params || !x0 || !x_out || !verdict) return fail(SCO_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
   const int n = h->S.n;
   cudaStream_t st = (cudaStream_t)stream;
-  sco_handle::Staging &g = h->stg[h->next_stg++ % sco_handle::NSLOT];
+  sco_handle::Staging &g = h->stg[h->next_stg++ % sco_handle::NSTG];
   if (B > g.cap_B) {
     CUDA_TRY(cudaEventSynchronize(g.done));  // nothing in flight may still use the old buffers
     int rc = 0;
     rc |= grow(&g.params, (size_t)B * h->S.stride); rc |= grow(&g.x0, (size_t)B * n);
     rc |= grow(&g.x, (size_t)B * n); rc |= grow(&g.merit, (size_t)B); rc |= grow(&g.obj, (size_t)B);
     rc |= grow(&g.vio, (size_t)B); rc |= grow(&g.verdict, (size_t)B); rc |= grow(&g.stats, (size_t)4 * B);
-    if (rc) return SCO_ERR_CUDA;
+    rc |= grow(&g.nonconv, (size_t)B);
+    if (rc) { g.cap_B = 0; return SCO_ERR_CUDA; }
     g.cap_B = B;
   }
   CUDA_TRY(cudaStreamWaitEvent(st, g.done, 0));
   CUDA_TRY(cudaMemcpyAsync(g.params, params, (size_t)B * h->S.stride * sizeof(double), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(g.x0, x0, (size_t)B * n * sizeof(double), cudaMemcpyHostToDevice, st));
-  int rc = sco_solve_batch(h, B, g.params, g.x0, s, g.x, g.verdict, g.merit, g.obj, g.vio, g.stats, st);
+  sco_batch_io io;
+  memset(&io, 0, sizeof(io));
+  io.d_params = g.params; io.d_x0 = g.x0; io.d_x_out = g.x; io.d_verdict = g.verdict; io.d_merit = g.merit;
+  io.d_objective = g.obj; io.d_max_vio = g.vio; io.d_stats = g.stats; io.d_nonconverged = nonconverged ? g.nonconv : nullptr;
+  int rc = sco_solve_batch_io(h, B, &io, s, st);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(x_out, g.x, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(verdict, g.verdict, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -444,6 +544,7 @@ extern "C" int sco_solve_batch_host_async(sco_handle *h, int64_t B, const double
   if (objective) CUDA_TRY(cudaMemcpyAsync(objective, g.obj, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (max_vio) CUDA_TRY(cudaMemcpyAsync(max_vio, g.vio, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (stats) CUDA_TRY(cudaMemcpyAsync(stats, g.stats, (size_t)4 * B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (nonconverged) CUDA_TRY(cudaMemcpyAsync(nonconverged, g.nonconv, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaEventRecord(g.done, st));
   return SCO_OK;
 }
@@ -468,9 +569,19 @@ extern "C" int sco_convexify(sco_handle *h, int64_t B, const double *d_params, c
   if (B <= 0) return SCO_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  ConvexifyArgs a = {(long long)B, d_params, d_x, d_f, d_J, d_b, d_obj, h->Jscr[0]};
+  // without d_J the kernel parks the Jacobian in a launch slot's scratch: take the slot like a solve does
+  double *scratch = nullptr;
+  int slot = -1;
+  if (!d_J) {
+    slot = (int)(h->next_slot++ % sco_handle::NSLOT);
+    CUDA_TRY(cudaStreamWaitEvent(st, h->slot_done[slot], 0));
+    scratch = h->Jscr[slot];
+  }
+  ConvexifyArgs a = {(long long)B, d_params, d_x, d_f, d_J, d_b, d_obj, scratch};
+  CUDA_TRY(h->gen_ops->prepare(h->carve_gen));
   h->gen_ops->convexify(stage_grid(h, B), h->smem_bytes, st, h->S, a);
   CUDA_TRY(cudaGetLastError());
+  if (slot >= 0) CUDA_TRY(cudaEventRecord(h->slot_done[slot], st));
   return SCO_OK;
 }
 
@@ -480,6 +591,16 @@ extern "C" int sco_qp_solve(sco_handle *h, int64_t B, const double *d_params, co
                             const double *d_xref, int use_penalty, int closest_point,
                             const sco_settings *s, double *d_xq, int32_t *d_status, int32_t *d_iters,
                             void *stream) {
+  return sco_qp_solve_w(h, B, d_params, d_J, d_b, d_mask, d_lbx, d_ubx, d_pi, d_kdup, nullptr, d_xref, use_penalty,
+                        closest_point, s, d_xq, d_status, d_iters, stream);
+}
+
+extern "C" int sco_qp_solve_w(sco_handle *h, int64_t B, const double *d_params, const double *d_J,
+                              const double *d_b, const uint32_t *d_mask, const double *d_lbx,
+                              const double *d_ubx, const double *d_pi, const int32_t *d_kdup,
+                              const double *d_wa, const double *d_xref, int use_penalty, int closest_point,
+                              const sco_settings *s, double *d_xq, int32_t *d_status, int32_t *d_iters,
+                              void *stream) {
   if (!h || !s || !d_params || !d_xq || !d_status || !d_iters) return fail(SCO_ERR_ARG, "null argument");
   if (use_penalty && h->S.m_nl > 0 && (!d_J || !d_b)) return fail(SCO_ERR_ARG, "penalty rows need J and b");
   if (closest_point && !d_xref) return fail(SCO_ERR_ARG, "closest_point needs xref");
@@ -487,8 +608,9 @@ extern "C" int sco_qp_solve(sco_handle *h, int64_t B, const double *d_params, co
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   DevSettings d = to_dev(s);
-  QpStageArgs a = {(long long)B, d_params, d_J, d_b, d_mask, d_lbx, d_ubx, d_pi, d_kdup, d_xref,
+  QpStageArgs a = {(long long)B, d_params, d_J, d_b, d_mask, d_lbx, d_ubx, d_pi, d_kdup, d_wa, d_xref,
                    use_penalty, closest_point, d_xq, d_status, d_iters};
+  CUDA_TRY(h->ops->prepare(h->carve_ops));
   h->ops->qp(stage_grid(h, B), h->smem_bytes, st, h->S, d, a);
   CUDA_TRY(cudaGetLastError());
   return SCO_OK;
@@ -502,6 +624,7 @@ extern "C" int sco_merit(sco_handle *h, int64_t B, const double *d_params, const
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   MeritArgs a = {(long long)B, d_params, d_x, d_J, d_b, d_mu, d_merit, d_model, d_max_vio, d_gv, d_gm};
+  CUDA_TRY(h->gen_ops->prepare(h->carve_gen));
   h->gen_ops->merit(stage_grid(h, B), h->smem_bytes, st, h->S, a);
   CUDA_TRY(cudaGetLastError());
   return SCO_OK;

@@ -396,6 +396,7 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
   const double *__restrict__ Jg = a_.Jg;
   const double *__restrict__ Qg = field_ptr(S_, S_.Q, a_.prm);
   const double *__restrict__ qg = field_ptr(S_, S_.q, a_.prm);
+  const double *__restrict__ qag = field_ptr(S_, S_.qa, a_.prm);
   const int o_lb = w_.lb.off, o_ub = w_.ub.off, o_bb = w_.bb.off, o_msk = w_.msk.off, o_x = w_.x.off, o_s = w_.s.off;
   const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sco_smem);
   const int half = tid >> 5;  // 0 / 1: the two warps split matrix rows
@@ -426,6 +427,7 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
   double c = 1.0;
   if (!rowwarp) {
     if (act && qg) qh = qg[lane];
+    if (act && qag) qh += a_.wa * qag[lane];
     sts_f64(sb + 8u * (DL::D + lane), 1.0);
   }
   __syncthreads();

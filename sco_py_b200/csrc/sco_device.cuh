@@ -96,6 +96,8 @@ struct DevStruct {
   int stage_per_warp;  // doubles
   long long stride;
   DevField Q, q, c, lin_l, lin_u;
+  DevField qa;         // AffExpr objective terms, summed (n): enters the QP with the weight of quirk C-4
+  DevField lb0, ub0;   // user bounds of the scalar variables (n each): the closest-point QP honours them
   DevField objp;       // non-quadratic objective: stack program (1 row)
   int obj_len, pad2_;  // its instruction count, 0 = none
   // linear rows: CSR + CSC (entry index into lin_val / Als)
@@ -139,6 +141,7 @@ struct DevSettings {
   double eps_abs, eps_rel, rho, sigma, alpha, eps_prim_inf, eps_dual_inf;
   int max_iter, scaling, check_termination, adaptive_rho, adaptive_rho_interval;
   int compound_penalty, freeze_sparsity, duplicate_rows, force_generic;
+  int aff_obj_quirk, warm_start;
 };
 
 __device__ __forceinline__ const double *field_ptr(const DevStruct &S, const DevField &f,

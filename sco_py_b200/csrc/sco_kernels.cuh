@@ -22,8 +22,13 @@ k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings
         const double *__restrict__ params, const double *__restrict__ x0, double *__restrict__ x_out,
         int *__restrict__ verdict, double *__restrict__ merit, double *__restrict__ objective,
         double *__restrict__ max_vio, int *__restrict__ stats, double *__restrict__ Jscr,
-        unsigned long long *counter, const int *__restrict__ order) {
+        unsigned long long *counter, const int *__restrict__ order, int *__restrict__ nonconv,
+        const int *__restrict__ order_err) {
   __shared__ long long next;
+  if (order_err && *order_err != 0) {  // sco_solve_batch_ordered: the order is not a permutation (checked by k_check_order)
+    for (long long b = (long long)blockIdx.x * TEAM + threadIdx.x; b < B; b += (long long)gridDim.x * TEAM) verdict[b] = -3;
+    return;
+  }
   QPW w;
   w.bind(S.L);
   const Sh xc = w.xc;  // n doubles appended after the layout
@@ -51,6 +56,7 @@ k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings
         stats[4 * b] = o.sqp_iters; stats[4 * b + 1] = o.qp_solves;
         stats[4 * b + 2] = o.admm_iters; stats[4 * b + 3] = o.last_status;
       }
+      if (nonconv) nonconv[b] = o.nonconv;
 #ifdef SCO_TIMING
       // diagnostic build only: the report slots carry the per-phase clock64() totals instead
       if (merit) merit[b] = (double)o.cyc_total;
@@ -101,7 +107,8 @@ __global__ void __maxnreg__(SCO_MAXNREG)
 k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st, long long B,
      const double *__restrict__ params, const double *__restrict__ J, const double *__restrict__ bvec,
      const uint32_t *__restrict__ mask, const double *__restrict__ lbx, const double *__restrict__ ubx,
-     const double *__restrict__ pi, const int *__restrict__ kdup, const double *__restrict__ xref,
+     const double *__restrict__ pi, const int *__restrict__ kdup, const double *__restrict__ wa,
+     const double *__restrict__ xref,
      int use_pen, int closest, double *__restrict__ xq, int *__restrict__ status,
      int *__restrict__ iters) {
   QPW w;
@@ -125,6 +132,8 @@ k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st
     a.Jg = use_pen ? J + b * S.jnnz : nullptr;
     a.pi = pi ? pi[b] : 0.0;
     a.kd = kdup ? (double)kdup[b] : 1.0;
+    a.wa = wa ? wa[b] : 1.0;
+    a.warm = 0;
     a.use_pen = use_pen;
     a.closest = closest;
     a.has_hq = 0;

@@ -15,6 +15,8 @@ struct SolveArgs {
   double *Jscr;
   unsigned long long *counter;
   const int *order;
+  int *nonconv;           // [B] or null
+  const int *order_err;   // != 0 on the device: `order` is not a permutation -> every verdict = -3, nothing solved
 };
 struct ConvexifyArgs {
   long long B;
@@ -27,6 +29,7 @@ struct QpStageArgs {
   const uint32_t *mask;
   const double *lbx, *ubx, *pi;
   const int *kdup;
+  const double *wa;
   const double *xref;
   int use_pen, closest;
   double *xq;
@@ -40,7 +43,8 @@ struct MeritArgs {
 
 struct TeamOps {
   int team;
-  cudaError_t (*configure)(size_t smem_bytes, int *occupancy);
+  cudaError_t (*configure)(size_t smem_bytes, int *occupancy, int *carveout);
+  cudaError_t (*prepare)(int carveout);  // re-applies the handle's carve-out before a launch (kernel attributes are shared)
   void (*solve)(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, const DevSettings &d,
                 const SolveArgs &a);
   void (*convexify)(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, const ConvexifyArgs &a);

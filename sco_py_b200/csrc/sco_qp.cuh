@@ -27,10 +27,12 @@ struct QPArgs {
   const double *Jg;   // unscaled Jacobian entries, global layout (may be null when !use_pen)
   double pi;          // slack cost (compounded penalty weight)
   double kd;          // copies of every penalty row
+  double wa;          // weight of the AffExpr objective terms (S.qa) in q
   int use_pen;        // 0: no penalty rows / slacks (closest feasible point)
   int closest;        // objective |x - xs|^2
   int has_hq;         // add the degree-2 model of a non-quadratic objective term (w.Hq, w.gq)
   int tail;           // the launch's work queue is drained: favour the latency of this problem (sco_dense.cuh)
+  int warm;           // same J, b, pi, kd as the previous solve of this team (only the box changed): reuse
 };
 
 struct QPResult {
@@ -156,11 +158,12 @@ struct QPSolver {
   // expects (unscaled): W_lb/W_ub bounds on x, W_bb = b, W_msk, W_xs (closest point target)
   __device__ __noinline__ void load_and_scale() {
     SCO_QP_LOCALS
-    const double *qg = field_ptr(SS, SS.q, a.prm);
+    const double *qg = field_ptr(SS, SS.q, a.prm), *qag = field_ptr(SS, SS.qa, a.prm);
     const double *llg = field_ptr(SS, SS.lin_l, a.prm), *ulg = field_ptr(SS, SS.lin_u, a.prm);
     for (int e = tid; e < n * n; e += TEAM) W_Sm[e] = psym(e / n, e % n);
     for (int j = tid; j < n; j += TEAM) {
-      W_qh[j] = a.closest ? -2.0 * W_xs[j] : (qg ? qg[j] : 0.0) + (a.has_hq ? W_gq[j] : 0.0);
+      W_qh[j] = a.closest ? -2.0 * W_xs[j]
+                          : (qg ? qg[j] : 0.0) + (qag ? a.wa * qag[j] : 0.0) + (a.has_hq ? W_gq[j] : 0.0);
       W_D[j] = 1.0;
       W_bx[j] = 1.0;
       W_Eb[j] = 1.0;

@@ -16,6 +16,7 @@ struct SqpOut {
   int verdict;
   double merit, objective, max_vio;
   int sqp_iters, qp_solves, admm_iters, last_status;
+  int nonconv;  // prob.nonconverged_groups of the last evaluation of solver.py:206-235 (bit g / bit 16+g)
 #ifdef SCO_TIMING
   long long cyc_total, cyc_setup, cyc_loop, cyc_check, cyc_cvx;  // clock64() ticks per phase
 #endif
@@ -44,12 +45,13 @@ struct SqpSolver {
   // quadratic part of the objective at xc: 0.5 x'Qx + q'x + c (QuadExpr.eval, expr.py:205-206)
   __device__ double objective_quad() {
     const double *Qg = field_ptr(S, S.Q, prm), *qg = field_ptr(S, S.q, prm), *cg = field_ptr(S, S.c, prm);
+    const double *qag = field_ptr(S, S.qa, prm);  // AffExpr objective terms: exact value a'x (expr.py:173-174)
     double v[1] = {0.0};
     for (int k = tid; k < n; k += TEAM) {
       double acc = 0.0;
       if (Qg)
         for (int j = 0; j < n; j++) acc += Qg[j * n + k] * xc[j];
-      v[0] += xc[k] * (0.5 * acc + (qg ? qg[k] : 0.0));
+      v[0] += xc[k] * (0.5 * acc + (qg ? qg[k] : 0.0) + (qag ? qag[k] : 0.0));
     }
     Team<TEAM>::reduce_sum(v, w.red);
     return v[0] + (cg ? cg[0] : 0.0);
@@ -211,7 +213,7 @@ struct SqpSolver {
   __device__ SqpOut run(const double *x0) {
     SqpOut o;
     o.verdict = 0; o.merit = 0; o.objective = 0; o.max_vio = 0;
-    o.sqp_iters = 0; o.qp_solves = 0; o.admm_iters = 0; o.last_status = 0;
+    o.sqp_iters = 0; o.qp_solves = 0; o.admm_iters = 0; o.last_status = 0; o.nonconv = 0;
 #ifdef SCO_TIMING
     o.cyc_setup = o.cyc_loop = o.cyc_check = o.cyc_cvx = 0;
     const long long t_run = clock64();
@@ -223,10 +225,17 @@ struct SqpSolver {
     bool finished = false;
     // ---- find_closest_feasible_point (prob.py:369-412): default OSQP settings (solver.py:81)
     {
-      for (int j = tid; j < n; j += TEAM) { w.xs[j] = xc[j]; w.lb[j] = -INFINITY; w.ub[j] = INFINITY; }
+      // bounds of the projection = whatever is on the scalar variables (osqp_utils.py:165-189): the user's
+      const double *lb0 = field_ptr(S, S.lb0, prm), *ub0 = field_ptr(S, S.ub0, prm);
+      for (int j = tid; j < n; j += TEAM) {
+        w.xs[j] = xc[j];
+        w.lb[j] = lb0 ? lb0[j] : -INFINITY;
+        w.ub[j] = ub0 ? ub0[j] : INFINITY;
+      }
       sync();
       QPArgs a;
-      a.prm = prm; a.Jg = nullptr; a.pi = 0.0; a.kd = 0.0; a.use_pen = 0; a.closest = 1; a.has_hq = 0; a.tail = 0;
+      a.prm = prm; a.Jg = nullptr; a.pi = 0.0; a.kd = 0.0; a.wa = 0.0; a.use_pen = 0; a.closest = 1; a.has_hq = 0; a.tail = 0;
+      a.warm = 0;
       DevSettings d = st;
       d.eps_abs = 1e-6; d.eps_rel = 1e-9; d.max_iter = 100000; d.rho = 0.1; d.sigma = 5e-10;
       d.adaptive_rho = 0;
@@ -241,6 +250,7 @@ struct SqpSolver {
       }
     }
     double pi = 1.0, kd = 0.0;
+    double wa = 0.0;  // weight of the AffExpr objective terms in the QP (quirk C-4)
     bool mask_set = false;
     if (!finished) {
       bool success = false;
@@ -262,6 +272,8 @@ struct SqpSolver {
 #endif
           kd = st.duplicate_rows ? kd + 1.0 : 1.0;      // prob.py:508-509
           pi = st.compound_penalty ? pi * mu : mu;      // prob.py:424-426
+          wa = st.aff_obj_quirk ? (wa + 1.0) * mu : 1.0;  // prob.py:220-221,240-249 then :424-426
+          bool first_qp = true;  // of this convexification (warm start, sco_settings.warm_start)
           violation_sums(vs);
           const double merit = objective() + mu * vs[0];
           double mvec[SCO_DEV_MAX_GROUPS];
@@ -272,7 +284,9 @@ struct SqpSolver {
             for (int j = tid; j < n; j += TEAM) { w.lb[j] = w.xs[j] - delta; w.ub[j] = w.xs[j] + delta; }
             sync();
             QPArgs a;
-            a.prm = prm; a.Jg = Jg; a.pi = pi; a.kd = kd; a.use_pen = 1; a.closest = 0; a.has_hq = S.obj_len != 0;
+            a.prm = prm; a.Jg = Jg; a.pi = pi; a.kd = kd; a.wa = wa; a.use_pen = 1; a.closest = 0; a.has_hq = S.obj_len != 0;
+            a.warm = (st.warm_start && !first_qp) ? 1 : 0;
+            first_qp = false;
             // one thread looks at the queue and the team agrees on the answer (a per-thread read could
             // split the team at the moment the queue runs dry)
             if (tid == 0)
@@ -304,18 +318,20 @@ struct SqpSolver {
             if (approx < -1e-5) { restore = true; ret = true; retval = false; }          // _bad_model
             else if (approx < st.min_approx_improve) { restore = true; ret = true; retval = true; }  // _y_converged
             else {
-              bool nonconv = false;  // solver.py:209-235
+              int ma = 0, mb = 0;  // solver.py:209-235: first loop (with the overlap rule), second loop (without)
               for (int g = 0; g < ng; g++) {
                 const double av = mvec[g] - ms_[2 + g];
                 if (mvec[g] > st.cnt_tolerance && av < st.min_approx_improve) {
+                  mb |= 1 << g;
                   bool ov = false;
                   for (int g2 = 0; g2 < ng; g2++)
                     if (g2 != g && ((S.overlap[g] >> g2) & 1) && (mvec[g2] - ms_[2 + g2]) > st.min_approx_improve)
                       ov = true;
-                  if (!ov) nonconv = true;
+                  if (!ov) ma |= 1 << g;
                 }
               }
-              if (nonconv) { restore = true; ret = true; retval = true; }
+              o.nonconv = ma ? (ma | (mb << 16)) : 0;  // the reference clears the list at every evaluation
+              if (ma) { restore = true; ret = true; retval = true; }
             }
             if (ret) {
               for (int j = tid; j < n; j += TEAM) xc[j] = w.xs[j];

@@ -67,6 +67,7 @@ class Engine(object):
         cs.Q, cs.q, cs.c = _field(st.Q), _field(st.q), _field(st.c)
         cs.lin_l, cs.lin_u = _field(st.lin_l), _field(st.lin_u)
         cs.obj_prog, cs.obj_prog_len = _field(st.obj_prog), int(st.obj_prog_len)
+        cs.qa, cs.lb0, cs.ub0 = _field(st.qa), _field(st.lb0), _field(st.ub0)
         if st.m_lin:
             cs.lin_rowptr = hold(st.lin_rowptr, np.int32)
             cs.lin_col = hold(st.lin_col, np.int32)
@@ -124,13 +125,15 @@ class Engine(object):
             obj = torch.empty_like(merit)
             vio = torch.empty_like(merit)
             stats = torch.empty((B, 4), dtype=torch.int32, device=self.device)
+            nonconv = torch.empty(B, dtype=torch.int32, device=self.device)
             if order is not None:
                 order = order.to(self.device, torch.int32).contiguous()
                 assert order.numel() == B
-            _lib.check(self.lib.sco_solve_batch_ordered(self.h, B, _ptr(params), _ptr(x0), ctypes.byref(settings),
-                                                        _ptr(x), _ptr(verdict), _ptr(merit), _ptr(obj), _ptr(vio),
-                                                        _ptr(stats), _ptr(order), self._stream()))
-        return dict(x=x, verdict=verdict, merit=merit, objective=obj, max_vio=vio, stats=stats)
+            io = _lib.CBatchIO(params.data_ptr(), x0.data_ptr(), x.data_ptr(), verdict.data_ptr(), merit.data_ptr(),
+                               obj.data_ptr(), vio.data_ptr(), stats.data_ptr(), nonconv.data_ptr(),
+                               order.data_ptr() if order is not None else None, None, None)
+            _lib.check(self.lib.sco_solve_batch_io(self.h, B, ctypes.byref(io), ctypes.byref(settings), self._stream()))
+        return dict(x=x, verdict=verdict, merit=merit, objective=obj, max_vio=vio, stats=stats, nonconverged=nonconv)
 
     def solve_batch_host(self, params, x0, settings, out=None, stream=None):
         """Host buffers in, host buffers out (copies inside): the end-to-end entry.  With `stream`
@@ -140,18 +143,16 @@ class Engine(object):
         B = x0.shape[0]
         if out is None:
             out = dict(x=np.empty_like(x0), verdict=np.empty(B, np.int32), merit=np.empty(B),
-                       objective=np.empty(B), max_vio=np.empty(B), stats=np.empty((B, 4), np.int32))
-        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
-        if stream is not None:
-            _lib.check(self.lib.sco_solve_batch_host_async(
-                self.h, B, vp(params), vp(x0), ctypes.byref(settings), vp(out["x"]), vp(out["verdict"]),
-                vp(out["merit"]), vp(out["objective"]), vp(out["max_vio"]), vp(out["stats"]),
-                ctypes.c_void_p(stream.cuda_stream)))
-            return out
-        _lib.check(self.lib.sco_solve_batch_host(self.h, B, vp(params), vp(x0), ctypes.byref(settings),
-                                                 vp(out["x"]), vp(out["verdict"]), vp(out["merit"]),
-                                                 vp(out["objective"]), vp(out["max_vio"]),
-                                                 vp(out["stats"])))
+                       objective=np.empty(B), max_vio=np.empty(B), stats=np.empty((B, 4), np.int32),
+                       nonconverged=np.empty(B, np.int32))
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+        cs = ctypes.c_void_p(stream.cuda_stream) if stream is not None else ctypes.c_void_p(0)
+        _lib.check(self.lib.sco_solve_batch_host_groups(
+            self.h, B, vp(params), vp(x0), ctypes.byref(settings), vp(out["x"]), vp(out["verdict"]),
+            vp(out["merit"]), vp(out["objective"]), vp(out["max_vio"]), vp(out["stats"]),
+            vp(out.get("nonconverged")), cs))
+        if stream is None:  # the legacy stream: wait for it, like sco_solve_batch_host
+            torch.cuda.default_stream(self.device).synchronize()
         return out
 
     # ------------------------------------------------------------------ stages
@@ -167,20 +168,20 @@ class Engine(object):
         return f, J, b, obj
 
     def qp_solve(self, params, settings, J=None, b=None, mask=None, lbx=None, ubx=None, pi=None,
-                 kdup=None, xref=None, use_penalty=True, closest_point=False):
+                 kdup=None, xref=None, use_penalty=True, closest_point=False, wa=None):
         params = self._dev(params)
         B = params.shape[0]
-        J, b, lbx, ubx, pi, xref = [self._dev(a) for a in (J, b, lbx, ubx, pi, xref)]
+        J, b, lbx, ubx, pi, xref, wa = [self._dev(a) for a in (J, b, lbx, ubx, pi, xref, wa)]
         mask = self._dev(mask, torch.int32) if mask is not None else None
         kdup = self._dev(kdup, torch.int32) if kdup is not None else None
         nq = self.n_q if use_penalty else self.n
         xq = torch.empty((B, nq), dtype=torch.float64, device=self.device)
         status = torch.empty(B, dtype=torch.int32, device=self.device)
         iters = torch.empty(B, dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.sco_qp_solve(self.h, B, _ptr(params), _ptr(J), _ptr(b), _ptr(mask), _ptr(lbx),
-                                         _ptr(ubx), _ptr(pi), _ptr(kdup), _ptr(xref), int(use_penalty),
-                                         int(closest_point), ctypes.byref(settings), _ptr(xq),
-                                         _ptr(status), _ptr(iters), self._stream()))
+        _lib.check(self.lib.sco_qp_solve_w(self.h, B, _ptr(params), _ptr(J), _ptr(b), _ptr(mask), _ptr(lbx),
+                                           _ptr(ubx), _ptr(pi), _ptr(kdup), _ptr(wa), _ptr(xref), int(use_penalty),
+                                           int(closest_point), ctypes.byref(settings), _ptr(xq),
+                                           _ptr(status), _ptr(iters), self._stream()))
         return xq, status, iters
 
     def merit(self, params, x, mu, J=None, b=None):

@@ -92,7 +92,7 @@ class Prob(object):
             from ..engine import Engine
             st, params, x0, cps = batch.compile_batch([self])
             self._stage = dict(st=st, params=params, cp=cps[0], eng=Engine(st), J=None, b=None, mask=None,
-                               pi=1.0, kdup=0)
+                               pi=1.0, kdup=0, wa=0.0)
         return self._stage
 
     def _x(self):
@@ -132,6 +132,9 @@ class Prob(object):
     def update_obj(self, penalty_coeff=0.0):
         """Rebuilds the penalty objective for `penalty_coeff` (prob.py:414-426)."""
         s = self._dev()
+        # AffExpr objective terms are re-appended and every copy is scaled by the coefficient (quirk C-4,
+        # prob.py:220-221,240-249,424-426)
+        s["wa"] = (s["wa"] + 1.0) * penalty_coeff
         if s["st"].m_nl and s["J"] is not None:
             s["pi"] = s["pi"] * penalty_coeff   # prob.py:424-426: the stored weight is multiplied in place
             s["kdup"] += 1                      # prob.py:508-509: the penalty rows are appended again
@@ -158,7 +161,7 @@ class Prob(object):
                   kdup=np.array([s["kdup"]], np.int32)) if pen else {}
         xq, status, _ = s["eng"].qp_solve(s["params"], self._settings(
             eps_abs=osqp_eps_abs, eps_rel=osqp_eps_rel, max_iter=osqp_max_iter, rho=rho,
-            adaptive_rho=adaptive_rho, sigma=sigma), lbx=lb, ubx=ub, use_penalty=pen, **kw)
+            adaptive_rho=adaptive_rho, sigma=sigma), lbx=lb, ubx=ub, use_penalty=pen, wa=np.array([s["wa"]]), **kw)
         if int(status.cpu()[0]) not in (1, 2):
             return False
         self._deliver(xq.cpu().numpy()[0])

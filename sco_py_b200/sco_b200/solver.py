@@ -9,6 +9,15 @@ from .. import batch
 from . import osqp_utils
 
 
+def nonconverged_list(gids, mask):
+    """prob.nonconverged_groups as the reference leaves it (solver.py:209-235): the groups of the first loop in
+    gid2ind order (sorted ids, prob.py:538-542), then -- the reference appends again -- every violated group whose
+    model improvement is below the threshold, in sorted order.  `mask` is sco_batch_io.d_nonconverged."""
+    first = [g for k, g in enumerate(gids) if (mask >> k) & 1]
+    second = [g for k, g in enumerate(gids) if (mask >> (16 + k)) & 1]
+    return first + second if first else []
+
+
 class Solver(object):
     def __init__(self):
         self.improve_ratio_threshold = 0.25
@@ -61,7 +70,7 @@ class Solver(object):
             buckets.setdefault(batch.group_key(cp), []).append(i)
         B = len(probs)
         out = dict(x=[None] * B, verdict=np.zeros(B, np.int32), merit=np.zeros(B), objective=np.zeros(B),
-                   max_vio=np.zeros(B), stats=np.zeros((B, 4), np.int32))
+                   max_vio=np.zeros(B), stats=np.zeros((B, 4), np.int32), nonconverged=np.zeros(B, np.int32))
         for idx in buckets.values():
             st, params, x0, cps = batch.compile_batch([probs[i] for i in idx], compiled=[compiled[i] for i in idx])
             key = (batch.signature(st), device)
@@ -70,11 +79,14 @@ class Solver(object):
             res = self._engines[key].solve_batch_host(params, x0, settings)
             for k, i in enumerate(idx):
                 batch.scatter_solution(cps[k], res["x"][k])
-                probs[i].nonconverged_groups = []
+                probs[i].nonconverged_groups = nonconverged_list(cps[k].gids, int(res["nonconverged"][k]))
                 probs[i]._stage = None
                 out["x"][i] = res["x"][k]
-                for name in ("verdict", "merit", "objective", "max_vio", "stats"):
+                for name in ("verdict", "merit", "objective", "max_vio", "stats", "nonconverged"):
                     out[name][i] = res[name][k]
+                # prob.py:204 runs the callback after every successful QP, on the caller's thread; the whole SQP
+                # is one kernel here, so the hook runs once per problem when its result has been delivered
+                probs[i]._callback()
         self.last_report = out
         if verbose:
             print("sco_b200: %d problems, %d converged, mean ADMM iterations %.0f"

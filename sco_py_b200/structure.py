@@ -60,11 +60,14 @@ class Structure:
     lin_l: Field = field(default_factory=Field)   # m_lin
     lin_u: Field = field(default_factory=Field)   # m_lin
     blocks: List[Block] = field(default_factory=list)
-    n_groups: int = 1
+    n_groups: int = 1                             # 0 = no constraint is in any group (add_cnt_expr(..., group_ids=[]))
     group_overlap: Optional[np.ndarray] = None    # n_groups x n_groups 0/1 (prob.py:139-142)
     shared: Optional[np.ndarray] = None           # shared block
     obj_prog: Field = field(default_factory=Field)  # non-quadratic objective: stack program (sym.py), 1 row
     obj_prog_len: int = 0                           # its instruction count (0 = none)
+    qa: Field = field(default_factory=Field)        # n: summed A rows of AffExpr objective terms (quirk C-4 weight in the QP)
+    lb0: Field = field(default_factory=Field)       # n: user lower bounds of the scalar variables (closest-point QP)
+    ub0: Field = field(default_factory=Field)       # n: user upper bounds
 
     @property
     def m_nl(self):

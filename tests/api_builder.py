@@ -65,3 +65,36 @@ def build_prob(st, row, x0):
         cls = E.EqExpr if blk.cnt_type == CNT_EQ else E.LEqExpr
         prob.add_cnt_expr(E.BoundExpr(cls(family_expr(st, blk, row), val), var))
     return prob, var
+
+
+def build_qcqp_variant(i, n=8, m=6, aff=False, bounds=False, groups=None):
+    """QCQP i of the synthetic family (workloads.gen_qcqp) with optional extras of the reference API:
+    an AffExpr objective term (quirk C-4), user bounds on the scalar variables, constraint groups
+    (`groups` = list of (row slice, group ids))."""
+    from sco_py_b200 import workloads as W
+    st, params, x0 = W.gen_qcqp(1, n=n, m=m, first=i)
+    fam = family_expr(st, st.blocks[0], params[0])
+    val = np.asarray(st.get(st.blocks[0].val, params[0], m)).reshape(-1, 1)
+    rng = np.random.default_rng(900 + i)
+    prob = Prob()
+    ov = np.empty((n, 1), dtype=object)
+    for j in range(n):
+        if bounds:
+            lo = float(x0[0, j] - rng.uniform(-0.2, 1.0))  # the start value may lie outside its box
+            ov[j, 0] = OSQPVar("x%05d" % j, lo, lo + float(rng.uniform(0.1, 2.0)))
+        else:
+            ov[j, 0] = OSQPVar("x%05d" % j)
+        prob.add_osqp_var(ov[j, 0])
+    var = Variable(ov, x0[0].reshape(n, 1))
+    prob.add_var(var)
+    Q = np.asarray(st.get(st.Q, params[0], n * n)).reshape(n, n)
+    q = np.asarray(st.get(st.q, params[0], n)).reshape(1, n)
+    prob.add_obj_expr(E.BoundExpr(E.QuadExpr(Q, q, np.zeros((1, 1))), var))
+    if aff:
+        prob.add_obj_expr(E.BoundExpr(E.AffExpr(0.3 * rng.standard_normal((1, n)), np.array([[0.25]])), var))
+    if groups is None:
+        prob.add_cnt_expr(E.BoundExpr(E.LEqExpr(fam, val), var))
+    else:
+        for sl, gids in groups:
+            prob.add_cnt_expr(E.BoundExpr(E.LEqExpr(E.QuadFormExpr(fam.P[sl], fam.a[sl]), val[sl]), var), group_ids=gids)
+    return prob, var
