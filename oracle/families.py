@@ -77,20 +77,30 @@ FK7_ALPHA = np.array([0.0, -np.pi / 2, np.pi / 2, np.pi / 2, -np.pi / 2, np.pi /
 FK7_FLANGE = 0.107
 
 
+_FK7_CA = [float(v) for v in np.cos(FK7_ALPHA)]
+_FK7_SA = [float(v) for v in np.sin(FK7_ALPHA)]
+
+
 def fk7_pos(qj):
-    """qj (7,) -> (3,) flange position.  T_i = Rx(alpha_i) Tx(a_i) Rz(q_i) Tz(d_i)."""
-    R = np.eye(3)
-    p = np.zeros(3)
+    """qj (7,) -> (3,) flange position.  T_i = Rx(alpha_i) Tx(a_i) Rz(q_i) Tz(d_i).
+
+    Scalar arithmetic in a FIXED order -- every product rounded on its own, three-term sums left to right --
+    so that the CUDA kernel (sco_families.cuh: fk7_pos with __dmul_rn / __dadd_rn) performs the very same
+    operations and the two sides differ only through sin / cos.  (A BLAS-backed `R @ v` sums in an order that
+    depends on the library build; profiles/arm_sensitivity.py shows that differences of ~10 ulp in f are enough
+    to make the SQP of an occasional arm problem stop one iteration earlier or later.)"""
+    import math
+    R = [[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]
+    p = [0.0, 0.0, 0.0]
     for i in range(7):
-        ca, sa = np.cos(FK7_ALPHA[i]), np.sin(FK7_ALPHA[i])
-        ct, st = np.cos(qj[i]), np.sin(qj[i])
-        Ri = np.array([[ct, -st, 0.0],
-                       [st * ca, ct * ca, -sa],
-                       [st * sa, ct * sa, ca]])
-        pi = np.array([FK7_A[i], -sa * FK7_D[i], ca * FK7_D[i]])
-        p = p + R @ pi
-        R = R @ Ri
-    return p + R @ np.array([0.0, 0.0, FK7_FLANGE])
+        ca, sa = _FK7_CA[i], _FK7_SA[i]
+        qi = float(qj[i])
+        st, ct = math.sin(qi), math.cos(qi)
+        Ri = [[ct, -st, 0.0], [st * ca, ct * ca, -sa], [st * sa, ct * sa, ca]]
+        pi = [float(FK7_A[i]), -sa * float(FK7_D[i]), ca * float(FK7_D[i])]
+        p = [p[r] + ((R[r][0] * pi[0] + R[r][1] * pi[1]) + R[r][2] * pi[2]) for r in range(3)]
+        R = [[(R[r][0] * Ri[0][c] + R[r][1] * Ri[1][c]) + R[r][2] * Ri[2][c] for c in range(3)] for r in range(3)]
+    return np.array([p[r] + ((R[r][0] * 0.0 + R[r][1] * 0.0) + R[r][2] * FK7_FLANGE) for r in range(3)])
 
 
 def fk7_f(x):

@@ -38,16 +38,28 @@ def _units():
 
 def build(force=False, verbose=False):
     deps = _deps()
+    # extra flags (e.g. -DSCO_TIMING, whose kernels overwrite result slots with cycle counts) are part of what a
+    # build is: objects compiled under other flags are never reused
+    flags = os.environ.get("SCO_NVCC_FLAGS", "").strip()
+    stamp = os.path.join(OBJ, "flags.stamp")
+    try:
+        same_flags = open(stamp).read() == flags
+    except OSError:
+        same_flags = not os.path.exists(OBJ) or not os.listdir(OBJ)
+    if not same_flags:
+        force = True
     if (not force and os.path.exists(LIB)
             and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in deps)):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
+    with open(stamp, "w") as f:
+        f.write(flags)
     base = [nvcc] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                             "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
         base += ["-Xptxas", "-v"]
-    base += os.environ.get("SCO_NVCC_FLAGS", "").split()  # e.g. -DSCO_TIMING for the clock64 experiment
+    base += flags.split()  # e.g. -DSCO_TIMING for the clock64 experiment
 
     def compile_one(u):
         obj, src, extra = u

@@ -67,6 +67,13 @@ __device__ void eval_circle2d(const DevStruct &S, const DevBlock &B, const doubl
 
 // ---- FK7: flange position of a 7-link modified-DH chain.  tab = a[7] d[7] cos(alpha)[7]
 // sin(alpha)[7] flange base_step ----
+// Every operation is rounded on its own (__dmul_rn / __dadd_rn are never contracted into FMAs) and three-term
+// sums run left to right: the very sequence of oracle/families.py:fk7_pos, so that the two sides differ only
+// through sin / cos.  profiles/arm_sensitivity.py: ~10 ulp of difference in f make the SQP of an occasional
+// arm problem stop one iteration earlier or later (|dx| ~ 1e-3); ~1 ulp does not.
+__device__ __forceinline__ double dot3_rn(double a0, double b0, double a1, double b1, double a2, double b2) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
 __device__ __forceinline__ void fk7_pos(const double *q, const double *tab, double out[3]) {
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   double p[3] = {0, 0, 0};
@@ -74,17 +81,18 @@ __device__ __forceinline__ void fk7_pos(const double *q, const double *tab, doub
     const double ai = tab[i], di = tab[7 + i], ca = tab[14 + i], sa = tab[21 + i];
     double st, ct;
     sincos(q[i], &st, &ct);
-    const double Ri[9] = {ct, -st, 0.0, st * ca, ct * ca, -sa, st * sa, ct * sa, ca};
-    const double pi3[3] = {ai, -sa * di, ca * di};
-    for (int r = 0; r < 3; r++) p[r] = p[r] + (R[3 * r] * pi3[0] + R[3 * r + 1] * pi3[1] + R[3 * r + 2] * pi3[2]);
+    const double Ri[9] = {ct, -st, 0.0, __dmul_rn(st, ca), __dmul_rn(ct, ca), -sa, __dmul_rn(st, sa), __dmul_rn(ct, sa), ca};
+    const double pi3[3] = {ai, __dmul_rn(-sa, di), __dmul_rn(ca, di)};
+    for (int r = 0; r < 3; r++)
+      p[r] = __dadd_rn(p[r], dot3_rn(R[3 * r], pi3[0], R[3 * r + 1], pi3[1], R[3 * r + 2], pi3[2]));
     double Rn[9];
     for (int r = 0; r < 3; r++)
       for (int cc = 0; cc < 3; cc++)
-        Rn[3 * r + cc] = R[3 * r] * Ri[cc] + R[3 * r + 1] * Ri[3 + cc] + R[3 * r + 2] * Ri[6 + cc];
+        Rn[3 * r + cc] = dot3_rn(R[3 * r], Ri[cc], R[3 * r + 1], Ri[3 + cc], R[3 * r + 2], Ri[6 + cc]);
     for (int e = 0; e < 9; e++) R[e] = Rn[e];
   }
   const double fl = tab[28];
-  for (int r = 0; r < 3; r++) out[r] = p[r] + (R[3 * r] * 0.0 + R[3 * r + 1] * 0.0 + R[3 * r + 2] * fl);
+  for (int r = 0; r < 3; r++) out[r] = __dadd_rn(p[r], dot3_rn(R[3 * r], 0.0, R[3 * r + 1], 0.0, R[3 * r + 2], fl));
 }
 
 // Central differences at steps h and 2h, Richardson-combined -- the scheme of

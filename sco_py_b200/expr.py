@@ -407,6 +407,10 @@ class SymExpr(DeviceFamilyExpr):
         self.rows = list(rows)
         self.m = len(self.rows)
         self.program, self.n_instr = sym.compile_rows(self.rows)
+        ins = self.program[self.m:].reshape(-1, 2)
+        used = ins[ins[:, 0] == sym.PUSH_X, 1]
+        if used.size and (used.min() < 0 or used.max() >= self.n):  # the device would read past x
+            raise ValueError("SymExpr over %d variables uses variable index %d" % (self.n, int(used.max())))
         self.jw = self.n
         self.ipar = [self.n, self.m, self.n_instr, 0, 0, 0, 0, 0]
         Expr.__init__(self, self._f, None)

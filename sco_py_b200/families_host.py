@@ -23,13 +23,20 @@ def fk7_table():
 
 
 def fk7_pos(qj):
-    R = np.eye(3)
-    p = np.zeros(3)
-    ca_, sa_ = np.cos(FK7_ALPHA), np.sin(FK7_ALPHA)
+    """Flange position of the chain for joint angles qj (7,).  Plain scalar arithmetic, one rounding per
+    operation, in the order the kernel uses (sco_families.cuh: fk7_pos), so host and device agree up to
+    sin / cos."""
+    import math
+    ca_ = [float(v) for v in np.cos(FK7_ALPHA)]
+    sa_ = [float(v) for v in np.sin(FK7_ALPHA)]
+    R = [[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]
+    p = [0.0, 0.0, 0.0]
     for i in range(7):
         ca, sa = ca_[i], sa_[i]
-        ct, st = np.cos(qj[i]), np.sin(qj[i])
-        Ri = np.array([[ct, -st, 0.0], [st * ca, ct * ca, -sa], [st * sa, ct * sa, ca]])
-        p = p + R @ np.array([FK7_A[i], -sa * FK7_D[i], ca * FK7_D[i]])
-        R = R @ Ri
-    return p + R @ np.array([0.0, 0.0, FK7_FLANGE])
+        th = float(qj[i])
+        sn, cs = math.sin(th), math.cos(th)
+        Ri = [[cs, -sn, 0.0], [sn * ca, cs * ca, -sa], [sn * sa, cs * sa, ca]]
+        off = [float(FK7_A[i]), -sa * float(FK7_D[i]), ca * float(FK7_D[i])]
+        p = [p[r] + ((R[r][0] * off[0] + R[r][1] * off[1]) + R[r][2] * off[2]) for r in range(3)]
+        R = [[(R[r][0] * Ri[0][c] + R[r][1] * Ri[1][c]) + R[r][2] * Ri[2][c] for c in range(3)] for r in range(3)]
+    return np.array([p[r] + ((R[r][0] * 0.0 + R[r][1] * 0.0) + R[r][2] * FK7_FLANGE) for r in range(3)])

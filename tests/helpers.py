@@ -84,3 +84,25 @@ def split_J(st, Jflat):
         out.append(dense_J(st, bi, Jflat[off:off + cnt]))
         off += cnt
     return out
+
+
+def _port_job(job):
+    name, index, solver, quirks = job
+    from sco_py_b200 import workloads as W
+    st, params, x0 = W.GENERATORS[name](1, first=index)
+    r = sqp_port.solve(st, params[0], x0[0], solver=solver, quirks=quirks)
+    r.pop("trace", None)
+    return index, r
+
+
+def port_solve_many(name, indices, solver, quirks=None, workers=None):
+    """The oracle port on problems `indices` of config `name`, one process per core (the port is single-threaded and
+    a heavy-tailed problem can take a minute).  -> {index: result}"""
+    import multiprocessing as mp
+    import os
+    jobs = [(name, int(i), solver, quirks) for i in indices]
+    workers = workers or min(len(jobs), os.cpu_count() or 1)
+    if workers <= 1:
+        return dict(_port_job(j) for j in jobs)
+    with mp.get_context("fork").Pool(workers) as pool:
+        return dict(pool.imap_unordered(_port_job, jobs, chunksize=1))

@@ -78,9 +78,14 @@ def test_unsupported_inputs_fail_loudly():
     p.add_cnt_expr(E.BoundExpr(E.LEqExpr(E.Expr(lambda x: x[:1] ** 2), np.zeros((1, 1))), var))
     with pytest.raises(batch.UnsupportedProblem, match="black-box"):
         batch.compile_batch([p])
+    p = fresh()  # AffExpr objective terms are accepted (quirk C-4 weight on the device): their own field
+    p.add_obj_expr(E.BoundExpr(E.AffExpr(np.array([[1.0, 2.0], [0.5, 0.0]]), np.array([[0.25], [0.5]])), var))
+    st, params, _, _ = batch.compile_batch([p])
+    assert st.qa.off >= 0 and np.array_equal(params[0, st.qa.off:st.qa.off + 2], [1.5, 2.0])
+    assert params[0, st.c.off] == 0.75
     p = fresh()
-    p.add_obj_expr(E.BoundExpr(E.AffExpr(np.ones((1, 2)), np.zeros((1, 1))), var))
-    with pytest.raises(batch.UnsupportedProblem, match="C-4"):
+    p.add_cnt_expr(E.BoundExpr(E.LEqExpr(E.QuadFormExpr(np.zeros((1, 3, 3)), np.ones((1, 3))), np.zeros((1, 1))), var))
+    with pytest.raises(batch.UnsupportedProblem, match="3 variables"):
         batch.compile_batch([p])
     with pytest.raises(NotImplementedError):
         fresh().add_cnt_expr(E.BoundExpr(E.LExpr(E.AffExpr(np.ones((1, 2)), np.zeros((1, 1))), np.ones((1, 1))), var))

@@ -21,7 +21,8 @@ from sco_py_b200 import workloads as W
 
 pytestmark = pytest.mark.gpu
 
-CONFIGS = [("qcqp", 6), ("point_robot", 4), ("arm", 4)]
+CONFIGS = [("qcqp", 64), ("point_robot", 16), ("arm", 16)]   # full solves (the oracle runs on every host core)
+STAGE_N = {"qcqp": 8, "point_robot": 4, "arm": 4}            # problems of the batch used by the stage-level tests
 X_TOL = {"qcqp": 1e-4, "point_robot": 1e-4, "arm": 2e-3}
 OBJ_TOL = {"qcqp": 1e-5, "point_robot": 1e-5, "arm": 1e-4}
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -51,7 +52,7 @@ def test_convexify_matches_oracle(engines, name):
     eng, st, params, x0 = engines[name]
     f, J, b, obj = [t.cpu().numpy() for t in eng.convexify(params, x0)]
     tol = 1e-7 if name == "arm" else 1e-9
-    for i in range(x0.shape[0]):
+    for i in range(min(x0.shape[0], 2 * STAGE_N[name])):
         pp = sqp_port.PortProblem(st, params[i], x0[i])
         pp.convexify()
         Jd = helpers.split_J(st, J[i])
@@ -66,15 +67,24 @@ def test_convexify_matches_oracle(engines, name):
 
 
 @pytest.mark.parametrize("name", [c[0] for c in CONFIGS])
-@pytest.mark.parametrize("kdup,pi,delta", [(1, 1.0, 1.0), (3, 10.0, 0.1), (7, 1000.0, 2e-5)])
-def test_qp_stage_matches_oracle(engines, name, kdup, pi, delta):
+@pytest.mark.parametrize("kdup,pi,delta,masked", [(1, 1.0, 1.0, False), (3, 10.0, 0.1, True), (7, 1000.0, 2e-5, True)])
+def test_qp_stage_matches_oracle(engines, name, kdup, pi, delta, masked):
+    """One penalty QP per problem.  `masked`: a non-trivial frozen-sparsity pattern (quirk C-2, prob.py:488-504):
+    a third of the stored Jacobian slots is switched off, on the device through d_mask and in the oracle's A."""
     eng, st, params, x0 = engines[name]
-    B = x0.shape[0]
+    B = STAGE_N[name]
+    params, x0 = params[:B], x0[:B]
     f, J, b, _ = eng.convexify(params, x0)
     Jn, bn = J.cpu().numpy(), b.cpu().numpy()
     lbx, ubx = x0 - delta, x0 + delta
-    xq, status, iters = eng.qp_solve(params, _settings(), J=J, b=b, lbx=lbx, ubx=ubx,
-                                     pi=np.full(B, pi), kdup=np.full(B, kdup, np.int32))
+    bits = None
+    if masked:
+        rng = np.random.default_rng(77)
+        keep = rng.random((B, st.m_nl, 32)) > 1.0 / 3.0
+        bits = (keep * (1 << np.arange(32, dtype=np.uint64))[None, None, :]).sum(axis=2).astype(np.uint32)
+    xq, status, iters = eng.qp_solve(params, _settings(), J=J, b=b, lbx=lbx, ubx=ubx, pi=np.full(B, pi),
+                                     kdup=np.full(B, kdup, np.int32),
+                                     mask=None if bits is None else bits.view(np.int32))
     xq, status, iters = xq.cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy()
     for i in range(B):
         Jd = helpers.split_J(st, Jn[i])
@@ -83,6 +93,17 @@ def test_qp_stage_matches_oracle(engines, name, kdup, pi, delta):
             bl.append(bn[i, r0:r0 + blk.m])
             r0 += blk.m
         masks = [np.ones_like(Jb, dtype=bool) for Jb in Jd]
+        if masked:  # bit s of row r <=> stored slot s of that row participates
+            r0 = 0
+            for bi, blk in enumerate(st.blocks):
+                cols = st.jac_cols(bi)
+                M = np.zeros_like(masks[bi])
+                for r in range(blk.m):
+                    for s_ in range(blk.jw):
+                        if (int(bits[i, r0 + r]) >> s_) & 1:
+                            M[r, cols[r, s_]] = True
+                masks[bi] = M
+                r0 += blk.m
         P, q, A, l, u = helpers.expand_qp(st, params[i], Jd, bl, masks, lbx[i], ubx[i], pi, kdup)
         res = helpers.oracle_qp(P, q, A, l, u)
         assert status[i] == res.info.status_val, (i, status[i], res.info.status_val, iters[i], res.info.iter)
@@ -95,7 +116,8 @@ def test_qp_stage_matches_oracle(engines, name, kdup, pi, delta):
 @pytest.mark.parametrize("name", [c[0] for c in CONFIGS])
 def test_closest_point_qp_matches_oracle(engines, name):
     eng, st, params, x0 = engines[name]
-    B = x0.shape[0]
+    B = STAGE_N[name]
+    params, x0 = params[:B], x0[:B]
     xq, status, iters = eng.qp_solve(params, _settings(), xref=x0, use_penalty=False, closest_point=True)
     xq, status, iters = xq.cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy()
     inf = np.full(st.n, np.inf)
@@ -117,8 +139,9 @@ def test_full_solve_matches_port(engines, name):
     vio = out["max_vio"].cpu().numpy()
     obj = out["objective"].cpu().numpy()
     stats = out["stats"].cpu().numpy()
+    refs = helpers.port_solve_many(name, range(x0.shape[0]), W.SOLVER_SETTINGS)
     for i in range(x0.shape[0]):
-        ref = sqp_port.solve(st, params[i], x0[i], solver=W.SOLVER_SETTINGS)
+        ref = refs[i]
         info = (name, i, stats[i].tolist(), ref["stats"])
         assert (verdict[i] == 1) == ref["success"], info
         err = np.abs(x[i] - ref["x"]).max()
@@ -247,7 +270,45 @@ def test_intended_semantics_mode_matches_the_port(engines):
     off = dict(compound_penalty=0, freeze_sparsity=0, duplicate_rows=0)
     out = eng.solve_batch(params, x0, _settings(**off))
     x, verdict = out["x"].cpu().numpy(), out["verdict"].cpu().numpy()
-    for i in range(x0.shape[0]):
-        ref = sqp_port.solve(st, params[i], x0[i], solver=W.SOLVER_SETTINGS, quirks={k: False for k in off})
+    refs = helpers.port_solve_many("qcqp", range(16), W.SOLVER_SETTINGS, quirks={k: False for k in off})
+    for i in range(16):
+        ref = refs[i]
         assert (verdict[i] == 1) == ref["success"], i
         assert np.abs(x[i] - ref["x"]).max() <= 1e-4 * max(1.0, np.abs(ref["x"]).max()), i
+
+
+def test_handles_of_one_team_size_do_not_disturb_each_other():
+    """Kernel attributes (dynamic shared-memory limit, carve-out) belong to the kernel, not to a handle: creating a
+    handle with a SMALLER working set of the same team size must not break launches of an earlier, larger one."""
+    from sco_py_b200.engine import Engine
+    st_big, p_big, x_big = W.gen_point_robot(4, T=40)
+    st_small, p_small, x_small = W.gen_point_robot(4, T=33)
+    big = Engine(st_big)
+    a = big.solve_batch(p_big, x_big, _settings())
+    small = Engine(st_small)
+    assert small.team == big.team and small.smem_bytes < big.smem_bytes
+    c = small.solve_batch(p_small, x_small, _settings())
+    b = big.solve_batch(p_big, x_big, _settings())  # round 1: cudaErrorInvalidValue here
+    d = small.solve_batch(p_small, x_small, _settings())
+    assert np.array_equal(a["x"].cpu().numpy(), b["x"].cpu().numpy())
+    assert np.array_equal(c["x"].cpu().numpy(), d["x"].cpu().numpy())
+    big.close()
+    small.close()
+
+
+def test_bad_processing_order_is_refused(engines):
+    """sco_solve_batch_ordered: an order that is not a permutation would solve some problems twice and skip
+    others; the device check turns the whole batch into SCO_VERDICT_BAD_ORDER instead."""
+    import torch
+    eng, st, params, x0 = engines["qcqp"]
+    B = 16
+    order = torch.arange(B, dtype=torch.int32)
+    order[3] = 5  # 5 twice, 3 never
+    out = eng.solve_batch(params[:B], x0[:B], _settings(), order=order)
+    assert (out["verdict"].cpu().numpy() == -3).all()
+    order[3] = B  # out of range
+    out = eng.solve_batch(params[:B], x0[:B], _settings(), order=order)
+    assert (out["verdict"].cpu().numpy() == -3).all()
+    good = eng.solve_batch(params[:B], x0[:B], _settings(), order=torch.arange(B - 1, -1, -1, dtype=torch.int32))
+    ref = eng.solve_batch(params[:B], x0[:B], _settings())
+    assert np.array_equal(good["x"].cpu().numpy(), ref["x"].cpu().numpy())
