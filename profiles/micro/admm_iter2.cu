@@ -217,6 +217,118 @@ __global__ void __maxnreg__(128) k_v3p(const double *M, const double *J, double 
 __global__ void __maxnreg__(96) k_v3p96(const double *M, const double *J, double *out, long long *cyc, int iters, Consts cs) { v3_body<1>(M, J, out, cyc, iters, cs); }
 __global__ void __maxnreg__(80) k_v3p80(const double *M, const double *J, double *out, long long *cyc, int iters, Consts cs) { v3_body<1>(M, J, out, cyc, iters, cs); }
 
+
+// ---------------------------------------------------------------- v5: fused mat-vec, REGISTER-TILED R rows x C columns per lane
+// Round-1 v0 delivers every vector entry to every lane: 64 lanes x 50 doubles = 25.6 KB from shared memory to
+// the register file per iteration (~100 wavefronts), and every variant so far saturates near 2.0 G
+// problem-iterations/s whatever its FP64 count.  Here a group of R lanes handles R rows: each lane multiplies a
+// C = ceil(50 / R)-column slice of those R rows (R x C matrix entries in registers, C vector entries loaded) and the
+// R partial sums are exchanged inside the group with log2(R) butterfly rounds, after which lane k of the group
+// holds the full dot product of "its" row -- so lane <-> row ownership, the update code and the single barrier per
+// iteration stay exactly as in v0.  Vector traffic drops by R.
+template <int R>
+__device__ __forceinline__ void v5_body(const double *M, double *out, long long *cyc, int iters, Consts cs) {
+  constexpr int C = ((NV + R - 1) / R + 1) & ~1;  // even: 128-bit loads
+  constexpr int VL = R * C + 2;
+  __shared__ __align__(16) double vb[2][VL];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool rowwarp = tid < 32;
+  const bool act = rowwarp ? lane < MP : lane < NP;
+  const int slot = rowwarp ? NP + lane : lane;   // my row of the iteration matrix
+  const int grp = lane & ~(R - 1), sub = lane & (R - 1);
+  double Mt[R][C];  // rows grp .. grp+R-1 of my warp's block, columns sub*C .. sub*C+C-1
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int row_lane = grp + r;
+    const bool ra = rowwarp ? row_lane < MP : row_lane < NP;
+    const int rs = rowwarp ? NP + row_lane : row_lane;
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+      const int col = sub * C + k;
+      Mt[r][k] = (ra && col < NV) ? M[(size_t)rs * NV + col] : 0.0;
+    }
+  }
+  const double sigma = cs.sigma, alpha = cs.alpha, oma = 1.0 - cs.alpha, rho = cs.rho, rhoi = 1.0 / cs.rho, kd = cs.kd;
+  double u0 = 0.01 * (lane + 1), u1 = rowwarp ? -1.0 : 1.0, u2 = 1.0, u3 = rowwarp ? 0.3 : 1.0 / rho;
+  double lo = rowwarp ? kd * u1 : -0.5, hi = 0.5, Mi = 0.7;
+  double p0 = 0, z0 = 0, y0 = 0, s = 0, zs = 0, ys = 0, g = Mi * (-u0);
+  for (int e = tid; e < 2 * VL; e += 64) (&vb[0][0])[e] = 0.0;
+  __syncthreads();
+  if (act) vb[0][slot] = -u0;
+  __syncthreads();
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(&vb[0][0]);
+  const unsigned off = 8u * (unsigned)(sub * C);
+  int p = 0;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+    const unsigned vcur = sb + (p ? 8u * VL : 0u) + off;
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0.0;
+    double acc2[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc2[r] = 0.0;
+#pragma unroll
+    for (int k = 0; k < C; k += 2) {
+      const double2 va = lds_v2(vcur + 8u * k);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        acc[r] = fma(Mt[r][k], va.x, acc[r]);
+        acc2[r] = fma(Mt[r][k + 1], va.y, acc2[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] += acc2[r];
+    // butterfly: after the round with distance d a lane keeps the rows whose bit d matches its own
+#pragma unroll
+    for (int d = R / 2; d >= 1; d >>= 1) {
+      const bool upper = (sub & d) != 0;
+#pragma unroll
+      for (int r = 0; r < d; r++) {
+        // rows [0, d) stay with the lower lanes, rows [d, 2d) go to the upper lanes
+        const double send = upper ? acc[r] : acc[r + d];
+        const double keep = upper ? acc[r + d] : acc[r];
+        acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+      }
+    }
+    const double a = acc[0];
+    double o;
+    if (rowwarp) {
+      const double stil = g - u3 * a;
+      const double sn = alpha * stil + oma * s;
+      const double ts = (alpha * u2) * stil + (oma * zs + ys * rhoi);
+      const double zns = relu_bits(ts);
+      ys = rho * (ts - zns);
+      const double zt = a + u1 * stil;
+      const double tz = alpha * zt + (oma * z0 + y0 * rhoi);
+      const double zn = tz < hi ? tz : hi;
+      y0 = rho * (tz - zn);
+      s = sn; zs = zns; z0 = zn;
+      const double wpen = rho * (2.0 * zn - tz);
+      const double r1 = (sigma * sn - u0) + u2 * (rho * (2.0 * zns - ts)) + lo * wpen;
+      g = Mi * r1;
+      o = kd * wpen - (rho * lo) * g;
+    } else {
+      const double xn = alpha * a + oma * p0;
+      const double tz = (alpha * u1) * a + (oma * z0 + y0 * u3);
+      const double zn = clampd(tz, lo, hi);
+      y0 = rho * (tz - zn);
+      p0 = xn; z0 = zn;
+      o = (sigma * xn - u0) + (u1 * rho) * (2.0 * zn - tz);
+    }
+    p ^= 1;
+    if (act) vb[p][slot] = o;
+    __syncthreads();
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * 64 + tid] = p0 + z0 + y0 + s + zs + ys + g;
+  if (tid == 0) cyc[blockIdx.x] = t1 - t0;
+}
+__global__ void __maxnreg__(255) k_v5r2(const double *M, double *out, long long *cyc, int iters, Consts cs) { v5_body<2>(M, out, cyc, iters, cs); }
+__global__ void __maxnreg__(255) k_v5r4(const double *M, double *out, long long *cyc, int iters, Consts cs) { v5_body<4>(M, out, cyc, iters, cs); }
+__global__ void __maxnreg__(255) k_v5r8(const double *M, double *out, long long *cyc, int iters, Consts cs) { v5_body<8>(M, out, cyc, iters, cs); }
+__global__ void __maxnreg__(168) k_v5r4_168(const double *M, double *out, long long *cyc, int iters, Consts cs) { v5_body<4>(M, out, cyc, iters, cs); }
+
 template <typename K, typename... A>
 void run(const char *name, K kern, int threads, double *out, long long *cyc, A... args) {
   int occ = 0;
@@ -249,9 +361,10 @@ int main() {
   cudaMalloc(&dM, NV * NV * 8); cudaMalloc(&out, 148 * 16 * 128 * 8); cudaMalloc(&cyc, 148 * 16 * 8);
   cudaMemcpy(dM, hM, NV * NV * 8, cudaMemcpyHostToDevice);
   run("v0 fused, 255 regs", k_v0, 64, out, cyc, (const double *)dM);
-  run("v3 split, var update early", k_v3, 64, out, cyc, (const double *)dM, (const double *)dM);
   run("v3 split, var || row update", k_v3p, 64, out, cyc, (const double *)dM, (const double *)dM);
-  run("v3 split, var || row, 96 regs", k_v3p96, 64, out, cyc, (const double *)dM, (const double *)dM);
-  run("v3 split, var || row, 80 regs", k_v3p80, 64, out, cyc, (const double *)dM, (const double *)dM);
+  run("v5 fused, tiled R=2", k_v5r2, 64, out, cyc, (const double *)dM);
+  run("v5 fused, tiled R=4", k_v5r4, 64, out, cyc, (const double *)dM);
+  run("v5 fused, tiled R=8", k_v5r8, 64, out, cyc, (const double *)dM);
+  run("v5 fused, tiled R=4, 168 regs", k_v5r4_168, 64, out, cyc, (const double *)dM);
   return 0;
 }

@@ -11,10 +11,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-LIB = os.path.join(PKG, "libsco_b200.so")
+# SCO_BUILD_TAG=<tag> builds a side-by-side variant (libsco_b200_<tag>.so, objects in build_<tag>/), e.g. the
+# cycle-counting diagnostic build:  SCO_BUILD_TAG=timing SCO_NVCC_FLAGS=-DSCO_TIMING python -m sco_py_b200.build
+# and load it with SCO_B200_LIB=.../libsco_b200_timing.so
+TAG = os.environ.get("SCO_BUILD_TAG", "")
+LIB = os.path.join(PKG, "libsco_b200%s.so" % ("_" + TAG if TAG else ""))
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "build")
-TEAMS = (32, 64, 128, 256)
+OBJ = os.path.join(PKG, "build" + ("_" + TAG if TAG else ""))
+TEAMS = (32, 64, 128, 256, 512)
 DENSE_KINDS = (1, 2, 3, 4)  # size table of the dense ADMM loop, see sco_create
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -108,10 +108,11 @@ static void build_layout(DevStruct &S, int team) {
   L.s = take(sl); L.Ds = take(sl); L.sl = take(sl); L.bs = take(sl); L.zs = take(sl); L.ys = take(sl);
   L.Es = take(sl); L.gs = take(sl); L.hs = take(sl); L.rs = take(sl); L.dss = take(sl); L.dys = take(sl);
   L.Minv = take(3 * mp);
-  L.red = take(8 * 16);
+  L.red = take(std::max(team / 32, 8) * 16);
   L.msk = take((mp + 1) / 2);
   L.stage = take(std::max((team / 32) * S.stage_per_warp, 100));
   L.Hq = take(S.obj_len ? n * n + 2 : 0); L.gq = take(S.obj_len ? n : 0);
+  L.ps = take(4 * n);
   L.total = off;
 }
 
@@ -333,6 +334,18 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   }
   std::vector<double> shared_v;
   if (desc->shared_len > 0 && desc->shared) shared_v.assign(desc->shared, desc->shared + desc->shared_len);
+  // pattern of Psym = (Q + Q') / 2 by column: exact for a shared Q, dense for a per-problem Q, empty without Q
+  std::vector<int> P_cptr(n + 1, 0), P_row;
+  if (desc->Q.off >= 0) {
+    for (int j = 0; j < n; j++) {
+      for (int i = 0; i < n; i++) {
+        bool nz = true;
+        if (desc->Q.shared) nz = shared_v[desc->Q.off + (size_t)i * n + j] != 0.0 || shared_v[desc->Q.off + (size_t)j * n + i] != 0.0;
+        if (nz) P_row.push_back(i);
+      }
+      P_cptr[j + 1] = (int)P_row.size();
+    }
+  }
   int rc = 0;
   rc |= upload(h, row_goff, &S.row_goff); rc |= upload(h, row_soff, &S.row_soff);
   rc |= upload(h, row_w, &S.row_w); rc |= upload(h, row_eq, &S.row_eq);
@@ -341,6 +354,26 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   rc |= upload(h, lrp, &S.lin_rowptr); rc |= upload(h, lcol, &S.lin_col); rc |= upload(h, lval, &S.lin_val);
   rc |= upload(h, lcptr, &S.lin_cptr); rc |= upload(h, lcentry, &S.lin_centry); rc |= upload(h, lcrow, &S.lin_crow);
   rc |= upload(h, shared_v, &S.shared);
+  rc |= upload(h, P_cptr, &S.P_cptr); rc |= upload(h, P_row, &S.P_row);
+  {
+    int bw = 0;
+    for (int j = 0; j < n; j++)
+      for (int p = P_cptr[j]; p < P_cptr[j + 1]; p++) bw = std::max(bw, std::abs(P_row[p] - j));
+    for (int r = 0; r < desc->m_lin; r++)
+      if (lrp[r + 1] > lrp[r]) {
+        int lo = n, hi = -1;
+        for (int p = lrp[r]; p < lrp[r + 1]; p++) { lo = std::min(lo, lcol[p]); hi = std::max(hi, lcol[p]); }
+        bw = std::max(bw, hi - lo);
+      }
+    for (int i = 0; i < m_nl; i++)
+      if (row_w[i] > 0) {
+        int lo = n, hi = -1;
+        for (int k = 0; k < row_w[i]; k++) { lo = std::min(lo, jcol[row_goff[i] + k]); hi = std::max(hi, jcol[row_goff[i] + k]); }
+        bw = std::max(bw, hi - lo);
+      }
+    if (S.obj_len) bw = n - 1;  // the degree-2 model of a non-quadratic objective is dense
+    S.s_bw = std::min(bw, n - 1);
+  }
   if (rc) { sco_destroy(h); return SCO_ERR_CUDA; }
   // ---- dense fast path: one dense hinge block, no linear rows, sizes within the instantiated table
   S.dense_kind = 0;
@@ -353,6 +386,13 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   // ---- team size and shared-memory layout
   const int work = std::max(std::max(n, m_nl), desc->m_lin);
   int team = work <= 40 ? 32 : work <= 96 ? 64 : work <= 192 ? 128 : 256;
+  {
+    // one thread per entity (variable / linear row / penalty row) is what the fast ADMM loop wants (sco_qp.cuh:
+    // fast_loop); structures with more than 512 entities stay on the strided shared-memory loop
+    // (every role starts on a warp boundary)
+    const int entities = ((n + 31) & ~31) + ((desc->m_lin + 31) & ~31) + ((m_nl + 31) & ~31);
+    if (entities <= 512) team = entities <= 32 ? 32 : entities <= 64 ? 64 : entities <= 128 ? 128 : entities <= 256 ? 256 : 512;
+  }
   if (S.dense_kind) team = 64;  // two warps per problem: rows | variables (sco_dense.cuh)
   for (;;) {
     build_layout(S, team);
@@ -363,7 +403,8 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
                 h->smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
   }
   h->team = team;
-  h->gen_ops = team == 32 ? sco_team_ops_32() : team == 64 ? sco_team_ops_64() : team == 128 ? sco_team_ops_128() : sco_team_ops_256();
+  h->gen_ops = team == 32 ? sco_team_ops_32() : team == 64 ? sco_team_ops_64() : team == 128 ? sco_team_ops_128()
+               : team == 256 ? sco_team_ops_256() : sco_team_ops_512();
   h->ops = h->gen_ops;
   if (S.dense_kind)
     h->ops = S.dense_kind == 1 ? sco_dense_ops_1() : S.dense_kind == 2 ? sco_dense_ops_2() : S.dense_kind == 3 ? sco_dense_ops_3() : sco_dense_ops_4();

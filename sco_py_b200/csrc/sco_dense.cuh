@@ -651,6 +651,7 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
   res.cyc_check = 0;
   for (int k = 0; k < 5; k++) res.cyc_c[k] = 0;
   res.cyc_setup = clock64() - t_begin;
+  res.cyc_scale = 0;
   const long long t_loop = clock64();
 #endif
   // ================================================================== ADMM

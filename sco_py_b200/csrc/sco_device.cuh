@@ -53,6 +53,7 @@ struct Layout {
   int msk;    // m_nl uint32 (counted in doubles, rounded up)
   int stage;  // per-warp staging buffers for family evaluation
   int Hq, gq;  // degree-2 model of a non-quadratic objective: H+ (n*n, then b at [n*n]), linear term (n)
+  int ps;     // partial sums of S^-1 rhs: 4 column segments x n (fast_loop, sco_qp.cuh)
   int total;  // doubles
 };
 
@@ -93,6 +94,8 @@ struct DevStruct {
   int n, m_lin, nnz_lin, n_blocks, n_groups, m_nl, n_slack, jnnz, n_q, nsl;
   int sjnnz;           // padded Jacobian entries in shared memory
   int dense_kind;      // != 0: two-warp dense solve (sco_dense.cuh), index into its size table
+  int s_bw;            // structural half-bandwidth of S = P + A'RA (max |i - j| over its pattern): the Gauss-Jordan
+                       // sweep of pivot k only touches the leading (k + s_bw + 1)^2 block
   int stage_per_warp;  // doubles
   long long stride;
   DevField Q, q, c, lin_l, lin_u;
@@ -111,6 +114,10 @@ struct DevStruct {
   const int *row_gmask;  // m_nl: constraint-group membership
   const int *jcol_g;     // jnnz: column of every stored entry (global layout)
   const int *pc_ptr, *pc_e, *pc_r;  // CSC over user variables: shared-memory entry index, row
+  // sparsity pattern of the symmetrised objective matrix, by column (exact when Q is shared by the batch -- the
+  // smoothness matrices of the trajectory configurations are block tridiagonal -- and dense otherwise; empty when
+  // there is no Q).  Column norms, P x and the assembly of S walk this instead of n entries per column.
+  const int *P_cptr, *P_row;
   const double *shared;
   int overlap[SCO_DEV_MAX_GROUPS];  // bit g2 of overlap[g] <=> groups overlap (prob.py:139-142)
   DevBlock blocks[SCO_DEV_MAX_BLOCKS];
@@ -126,11 +133,12 @@ struct DevIdx {
   const int *lin_rowptr, *lin_col, *lin_cptr, *lin_centry, *lin_crow;
   const double *lin_val;
   const int *row_goff, *row_soff, *row_w, *row_eq, *row_gmask, *jcol_g, *pc_ptr, *pc_e, *pc_r;
+  const int *P_cptr, *P_row;
   __device__ __forceinline__ explicit DevIdx(const DevStruct &S)
       : n(S.n), m_lin(S.m_lin), nnz_lin(S.nnz_lin), m_nl(S.m_nl), n_slack(S.n_slack), lin_rowptr(S.lin_rowptr),
         lin_col(S.lin_col), lin_cptr(S.lin_cptr), lin_centry(S.lin_centry), lin_crow(S.lin_crow), lin_val(S.lin_val),
         row_goff(S.row_goff), row_soff(S.row_soff), row_w(S.row_w), row_eq(S.row_eq), row_gmask(S.row_gmask),
-        jcol_g(S.jcol_g), pc_ptr(S.pc_ptr), pc_e(S.pc_e), pc_r(S.pc_r) {}
+        jcol_g(S.jcol_g), pc_ptr(S.pc_ptr), pc_e(S.pc_e), pc_r(S.pc_r), P_cptr(S.P_cptr), P_row(S.P_row) {}
 };
 
 struct DevSettings {
@@ -253,6 +261,7 @@ struct QPW {
   ShU32 msk;
   Sh stage;
   Sh Hq, gq;
+  Sh ps;
   Sh xc;  // current SQP iterate, n doubles appended after the layout
 
   __device__ __forceinline__ void bind(const Layout &L) {
@@ -271,6 +280,7 @@ struct QPW {
     msk = ShU32{L.msk};
     stage = Sh{L.stage};
     Hq = Sh{L.Hq}; gq = Sh{L.gq};
+    ps = Sh{L.ps};
     xc = Sh{L.total};
   }
 };

@@ -14,7 +14,14 @@
 #ifndef SCO_DK
 #define SCO_DK 0
 #endif
+#if defined(SCO_TEAM) && SCO_TEAM >= 256
+// A warp's registers come out of its SM sub-partition's 16,384: a 512-thread team has four warps on each, so 128
+// registers per thread is its ceiling (a 448-thread team has the same problem: 4 + 4 + 3 + 3 warps); a 256-thread
+// team at 128 registers fits two teams per SM, which overlaps the barrier-bound phases of two problems.
+#define SCO_MAXNREG 128
+#else
 #define SCO_MAXNREG 255
+#endif
 
 template <int TEAM, int DK>
 __global__ void __maxnreg__(SCO_MAXNREG)
@@ -159,6 +166,7 @@ k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st
 #ifdef SCO_TIMING
       xq[b * nq] = (double)r.cyc_loop; xq[b * nq + 1] = (double)r.cyc_check; xq[b * nq + 2] = (double)r.cyc_setup;
       for (int k = 0; k < 5; k++) xq[b * nq + 3 + k] = (double)r.cyc_c[k];
+      xq[b * nq + 8] = (double)r.cyc_scale;
 #endif
     }
     Team<TEAM>::sync();

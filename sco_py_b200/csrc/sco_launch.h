@@ -57,6 +57,7 @@ const TeamOps *sco_team_ops_32();
 const TeamOps *sco_team_ops_64();
 const TeamOps *sco_team_ops_128();
 const TeamOps *sco_team_ops_256();
+const TeamOps *sco_team_ops_512();
 // dense kinds (two-warp register-resident ADMM loop, sco_dense.cuh); convexify / merit are null
 const TeamOps *sco_dense_ops_1();
 const TeamOps *sco_dense_ops_2();

@@ -40,7 +40,8 @@ struct QPResult {
   double pri_res, dua_res;
 #ifdef SCO_TIMING
   long long cyc_loop, cyc_check, cyc_setup;  // clock64() ticks: ADMM loop (incl. checks), checks, setup
-  long long cyc_c[5];                        // stages of the termination test
+  long long cyc_c[5];                        // stages of the termination test / phases of the generic loops
+  long long cyc_scale;                       // generic setup: load + Ruiz (the rest of cyc_setup is S and its inverse)
 #endif
 };
 
@@ -107,11 +108,11 @@ struct QPSolver {
       W_bb = w.bb, W_fv = w.fv, W_dyp = w.dyp, W_s = w.s, W_Ds = w.Ds, W_sl = w.sl, W_bs = w.bs,            \
       W_zs = w.zs, W_ys = w.ys, W_Es = w.Es, W_gs = w.gs, W_hs = w.hs, W_rs = w.rs, W_dss = w.dss,          \
       W_dys = w.dys, W_Minv = w.Minv, W_red = w.red, W_stage = w.stage, W_Hq = w.Hq, W_gq = w.gq,           \
-      W_xc = w.xc;                                                                                          \
+      W_xc = w.xc, W_ps = w.ps;                                                                             \
   const ShU32 W_msk = w.msk;                                                                                \
   (void)W_msk; (void)W_Js; (void)W_Sm; (void)W_Als; (void)W_x; (void)W_xt; (void)W_xt2; (void)W_qh; (void)W_D; (void)W_bx; (void)W_rb; (void)W_lb; (void)W_ub; (void)W_zb; (void)W_yb; (void)W_Eb; (void)W_dxv; (void)W_dyb; (void)W_xs; (void)W_El; (void)W_rl;\
   (void)W_ll; (void)W_ul; (void)W_zl; (void)W_yl; (void)W_wl; (void)W_dyl; (void)W_Ep; (void)W_rp; (void)W_lp; (void)W_up; (void)W_zp; (void)W_yp; (void)W_wp; (void)W_bb; (void)W_fv; (void)W_dyp; (void)W_s; (void)W_Ds; (void)W_sl; (void)W_bs;\
-  (void)W_zs; (void)W_ys; (void)W_Es; (void)W_gs; (void)W_hs; (void)W_rs; (void)W_dss; (void)W_dys; (void)W_Minv; (void)W_red; (void)W_stage; (void)W_Hq; (void)W_gq; (void)W_xc;\
+  (void)W_zs; (void)W_ys; (void)W_Es; (void)W_gs; (void)W_hs; (void)W_rs; (void)W_dss; (void)W_dys; (void)W_Minv; (void)W_red; (void)W_stage; (void)W_Hq; (void)W_gq; (void)W_xc; (void)W_ps;\
   const DevIdx S(this->S);                                                                                  \
   const DevSettings st = this->st;                                                                          \
   const QPArgs a = this->a;                                                                                 \
@@ -147,12 +148,29 @@ struct QPSolver {
     for (int k = 0; k < wd; k++) acc += W_Js[so + k] * v[__ldg(S.jcol_g + (go + k))];                                 \
     return acc;                                                                                             \
   };                                                                                                        \
+  /* column j of c D |Psym| D over the pattern of Psym (closest point: 2 I; objective model: dense) */        \
   auto pcol_norm = [&](int j) -> double {                                                                   \
     double cp = 0.0;                                                                                        \
-    for (int i = 0; i < n; i++) cp = fmax(cp, W_D[i] * fabs(W_Sm[i * n + j]));                              \
+    if (a.closest) cp = W_D[j] * fabs(W_Sm[j * n + j]);                                                     \
+    else if (a.has_hq) { for (int i = 0; i < n; i++) cp = fmax(cp, W_D[i] * fabs(W_Sm[i * n + j])); }       \
+    else for (int p = __ldg(S.P_cptr + j); p < __ldg(S.P_cptr + j + 1); p++) {                              \
+      const int i = __ldg(S.P_row + p);                                                                     \
+      cp = fmax(cp, W_D[i] * fabs(W_Sm[i * n + j]));                                                        \
+    }                                                                                                       \
     return cp * c * W_D[j];                                                                                 \
   };                                                                                                        \
-  (void)psym; (void)gatherAT; (void)lin_row_dot; (void)pen_row_dot; (void)pcol_norm;
+  /* (Psym v)_j for a variable-space vector v in shared memory */                                          \
+  auto psym_dot = [&](int j, Sh v) -> double {                                                              \
+    double px = 0.0;                                                                                        \
+    if (a.closest) px = 2.0 * v[j];                                                                         \
+    else if (a.has_hq) { for (int k = 0; k < n; k++) px += psym(k, j) * v[k]; }                             \
+    else if (Qg) for (int p = __ldg(S.P_cptr + j); p < __ldg(S.P_cptr + j + 1); p++) {                      \
+      const int k = __ldg(S.P_row + p);                                                                     \
+      px += 0.5 * (Qg[k * n + j] + Qg[j * n + k]) * v[k];                                                   \
+    }                                                                                                       \
+    return px;                                                                                              \
+  };                                                                                                        \
+  (void)psym; (void)gatherAT; (void)lin_row_dot; (void)pen_row_dot; (void)pcol_norm; (void)psym_dot;
 
   // ================================================================== setup
   // expects (unscaled): W_lb/W_ub bounds on x, W_bb = b, W_msk, W_xs (closest point target)
@@ -349,21 +367,31 @@ struct QPSolver {
       }
     }
     sync();
-    // in-place Gauss-Jordan inverse (S is SPD: no pivoting).  xt = pivot row, xt2 = pivot column
+    // in-place Gauss-Jordan inverse (S is SPD: no pivoting).  xt = pivot row, xt2 = pivot column.
+    // S is banded for trajectory structures (half-bandwidth s_bw): beyond row / column k + s_bw the pivot row and
+    // column of step k are still exact zeros, so the sweep only touches the leading mk x mk block (the same
+    // arithmetic on every element it changes, a third of the work for a narrow band).
+    const int bw = SS.s_bw;
     for (int k = 0; k < n; k++) {
+      const int mk = (k + bw + 1) < n ? (k + bw + 1) : n;
       const double d = 1.0 / W_Sm[k * n + k];
-      for (int j = tid; j < n; j += TEAM) {
+      for (int j = tid; j < mk; j += TEAM) {
         W_xt[j] = W_Sm[k * n + j] * d;
         W_xt2[j] = W_Sm[j * n + k];
       }
       sync();
-      for (int e = tid; e < n * n; e += TEAM) {
-        const int i = e / n, j = e % n;
+      int i = tid / mk, j = tid - i * mk;
+      const int di = TEAM / mk, dj = TEAM - di * mk;
+      while (i < mk) {
+        const int e = i * n + j;
         double v;
         if (i == k) v = (j == k) ? d : W_xt[j];
         else if (j == k) v = -W_xt2[i] * d;
         else v = W_Sm[e] - W_xt2[i] * W_xt[j];
         W_Sm[e] = v;
+        j += dj;
+        i += di;
+        if (j >= mk) { j -= mk; i++; }
       }
       sync();
     }
@@ -413,10 +441,7 @@ struct QPSolver {
       const double ax = W_bx[j] * W_x[j], ei = 1.0 / W_Eb[j], z = W_zb[j];
       v[0] = fmax(v[0], fabs((ax - z) * ei)); v[1] = fmax(v[1], fabs(z * ei)); v[2] = fmax(v[2], fabs(ax * ei));
       u[0] = fmax(u[0], fabs(ax - z)); u[1] = fmax(u[1], fabs(z)); u[2] = fmax(u[2], fabs(ax));
-      double px = 0.0;
-      if (a.closest) px = 2.0 * W_xt[j];
-      else if (Qg || a.has_hq)
-        for (int k = 0; k < n; k++) px += psym(k, j) * W_xt[k];
+      double px = psym_dot(j, W_xt);
       px *= c * W_D[j];
       const double aty = gatherAT(j, W_yl, W_wp) + W_bx[j] * W_yb[j];
       const double di = 1.0 / W_D[j], q = W_qh[j];
@@ -523,10 +548,7 @@ struct QPSolver {
     if (nv[0] > eps && qd[0] < -thr) {
       double pv[1] = {0.0};
       for (int j = tid; j < n; j += TEAM) {
-        double px = 0.0;
-        if (a.closest) px = 2.0 * W_xt[j];
-        else if (Qg || a.has_hq)
-          for (int k = 0; k < n; k++) px += psym(k, j) * W_xt[k];
+        const double px = psym_dot(j, W_xt);
         pv[0] = fmax(pv[0], fabs(c * px));  // Dinv .* (c D Psym D dx) = c * Psym (D dx)
       }
       Team<TEAM>::reduce_max(pv, W_red);
@@ -564,6 +586,302 @@ struct QPSolver {
     return res;
   }
 
+
+#ifdef SCO_TIMING
+#define SCO_PH(k) { sync(); const long long tq_ = clock64(); res.cyc_c[k] += tq_ - tph; tph = tq_; }
+#else
+#define SCO_PH(k)
+#endif
+
+  // ---- rare path of the fast loop, kept out of line (and out of its register budget): entries beyond the ones a
+  // thread keeps in registers.  which = 0: linear rows of a variable's column, 1: its penalty rows,
+  // 2: a linear row, 3: a penalty row (p2 = offset from the shared-memory to the global entry index)
+  __device__ __noinline__ double fast_overflow(int which, int p0, int p1, int p2, double acc) {
+    const QPW &wq = this->w;
+    const DevStruct &SS = this->S;
+    if (which == 0) for (int p = p0; p < p1; p++) acc = fma(wq.Als[__ldg(SS.lin_centry + p)], wq.wl[__ldg(SS.lin_crow + p)], acc);
+    else if (which == 1) for (int p = p0; p < p1; p++) acc = fma(wq.Js[__ldg(SS.pc_e + p)], wq.wp[__ldg(SS.pc_r + p)], acc);
+    else if (which == 2) for (int p = p0; p < p1; p++) acc = fma(wq.Als[p], wq.xt2[__ldg(SS.lin_col + p)], acc);
+    else for (int p = p0; p < p1; p++) acc = fma(wq.Js[p], wq.xt2[__ldg(SS.jcol_g + p + p2)], acc);
+    return acc;
+  }
+
+  // ================================================================== the ADMM loop, ONE THREAD PER ENTITY
+  // Same iteration as generic_loop below (same formulas in the same order; y / rho is y * (1 / rho) as in the
+  // reference's rho_inv_vec), different machine mapping: a thread owns ONE entity for the whole QP --
+  //   warps [0, nV)        variable j with its box row          (x, zb, yb)
+  //   warps [nV, nV + nL)  linear row r                         (z, y)
+  //   then nP warps        penalty row i with its one / two slacks
+  // (every role starts on a warp boundary) -- and keeps that entity's iterates AND constants in registers,
+  // including the first entries of its row of A (rows: SCO_EN) or of its column of A (variables: SCO_EH from
+  // linear rows + SCO_EH from penalty rows): coefficient + shared-memory index of the operand, padded with zero
+  // coefficients so that the products run without a branch -- an iteration touches no index array at all.
+  // generic_loop re-reads every constant from shared memory and every index from global memory in every iteration
+  // and strides TEAM threads over the entities (12,110 / 8,525 cycles per iteration for the arm / point robot;
+  // profiles/r1_cycles.txt).  S^-1 rhs is split over all threads (column segments, partial sums through shared
+  // memory).  Iterates go back to the shared-memory arrays only when the termination test runs (every
+  // check_termination iterations) or the loop ends, so check() / the certificates / the epilogue of solve() are
+  // shared with generic_loop.
+  // The three roles run three instantiations of fast_role<ROLE>, each with its own register allocation (one
+  // function holding the state of all three roles needs ~150 registers; a 512-thread team has 128).  All of them
+  // execute the same sequence of team barriers; the barrier only counts arrivals.
+  // Requires ceil32(n) + ceil32(m_lin) + ceil32(m_nl) <= TEAM and no adaptive rho.
+#define SCO_EN 6
+#define SCO_EH 3
+  struct FastCtx {
+    int id;        // index of the entity inside its role
+    int act;       // 0: padding lane of a role's last warp
+    int K3, j3, s3, c0, c1, p3_active;  // S^-1 rhs: column segment [c0, c1) of row j3
+  };
+
+  template <int ROLE>  // 0 variable, 1 linear row, 2 penalty row, 3 none (idle warps still do their share of S^-1 rhs)
+  __device__ __noinline__ int fast_role(const FastCtx f, int &iter_out, bool &checked_out, QPResult &res) {
+    SCO_QP_LOCALS
+    const double sigma = st.sigma, alpha = st.alpha, oma = 1.0 - st.alpha;
+    const double kd = a.kd;
+    const int id = f.id;
+    const bool act = f.act != 0;
+    // ---- entries.  Unused slots multiply the coefficient 0 with W_ps[0], which always holds a finite number.
+    double ec[SCO_EN];
+    int ea[SCO_EN];
+#pragma unroll
+    for (int k = 0; k < SCO_EN; k++) { ec[k] = 0.0; ea[k] = W_ps.off; }
+    int ovA0 = 0, ovA1 = 0, ovB0 = 0, ovB1 = 0, ovC = 0;  // entries beyond the register slots (rare)
+    // ---- state and constants of the entity
+    double x = 0.0, zb = 0.0, yb = 0.0, qh = 0.0, bx = 0.0, rb = 1.0, rbi = 1.0, lb = 0.0, ub = 0.0;   // variable
+    double z = 0.0, y = 0.0, rr = 1.0, rri = 1.0, lo = 0.0, hi = 0.0;                                   // row (lin / pen)
+    double mi11 = 0.0, mi12 = 0.0, mi22 = 0.0;                                                          // pen
+    double s1 = 0.0, zs1 = 0.0, ys1 = 0.0, sl1 = 0.0, bs1 = 0.0, rs1 = 1.0, rsi1 = 1.0, cd1 = 0.0, us1 = 0.0, hs1 = 0.0, g1 = 0.0;
+    double s2 = 0.0, zs2 = 0.0, ys2 = 0.0, sl2 = 0.0, bs2 = 0.0, rs2 = 1.0, rsi2 = 1.0, cd2 = 0.0, us2 = 0.0, hs2 = 0.0, g2 = 0.0;
+    int eq = 0;
+    if (ROLE == 0 && act) {
+      const int j = id;
+      qh = W_qh[j]; bx = W_bx[j]; rb = W_rb[j]; rbi = 1.0 / rb; lb = W_lb[j]; ub = W_ub[j];
+      int pl0 = 0, pl1 = 0, pp0 = 0, pp1 = 0;
+      if (m_lin) { pl0 = __ldg(S.lin_cptr + j); pl1 = __ldg(S.lin_cptr + j + 1); }
+      if (m_nl) { pp0 = __ldg(S.pc_ptr + j); pp1 = __ldg(S.pc_ptr + j + 1); }
+#pragma unroll
+      for (int k = 0; k < SCO_EH; k++) {
+        if (pl0 + k < pl1) {
+          ec[k] = W_Als[__ldg(S.lin_centry + pl0 + k)];
+          ea[k] = W_wl.off + __ldg(S.lin_crow + pl0 + k);
+        }
+        if (pp0 + k < pp1) {
+          ec[SCO_EH + k] = W_Js[__ldg(S.pc_e + pp0 + k)];
+          ea[SCO_EH + k] = W_wp.off + __ldg(S.pc_r + pp0 + k);
+        }
+      }
+      ovA0 = pl0 + SCO_EH; ovA1 = pl1; ovB0 = pp0 + SCO_EH; ovB1 = pp1;
+    } else if (ROLE == 1 && act) {
+      const int r = id;
+      rr = W_rl[r]; rri = 1.0 / rr; lo = W_ll[r]; hi = W_ul[r];
+      const int p0 = __ldg(S.lin_rowptr + r), p1 = __ldg(S.lin_rowptr + r + 1);
+#pragma unroll
+      for (int k = 0; k < SCO_EN; k++)
+        if (p0 + k < p1) { ec[k] = W_Als[p0 + k]; ea[k] = W_xt2.off + __ldg(S.lin_col + p0 + k); }
+      ovA0 = p0 + SCO_EN; ovA1 = p1;
+    } else if (ROLE == 2 && act) {
+      const int i = id;
+      const double cpi = c * a.pi;
+      eq = __ldg(S.row_eq + i);
+      rr = W_rp[i]; rri = 1.0 / rr; lo = W_lp[i]; hi = W_up[i];
+      mi11 = W_Minv[3 * i]; mi12 = W_Minv[3 * i + 1]; mi22 = W_Minv[3 * i + 2];
+      sl1 = W_sl[i]; bs1 = W_bs[i]; rs1 = W_rs[i]; rsi1 = 1.0 / rs1; cd1 = cpi * W_Ds[i]; us1 = OSQP_INFTY * W_Es[i]; hs1 = W_hs[i];
+      if (eq) {
+        const int i2 = ms + i;
+        sl2 = W_sl[i2]; bs2 = W_bs[i2]; rs2 = W_rs[i2]; rsi2 = 1.0 / rs2; cd2 = cpi * W_Ds[i2]; us2 = OSQP_INFTY * W_Es[i2]; hs2 = W_hs[i2];
+      }
+      const int so = __ldg(S.row_soff + i), go = __ldg(S.row_goff + i), wd = __ldg(S.row_w + i);
+#pragma unroll
+      for (int k = 0; k < SCO_EN; k++)
+        if (k < wd) { ec[k] = W_Js[so + k]; ea[k] = W_xt2.off + __ldg(S.jcol_g + go + k); }
+      ovA0 = so + SCO_EN; ovA1 = so + wd; ovC = go - so;  // overflow: W_Js[p], column jcol_g[p + ovC]
+    }
+    const bool overflow = ovA0 < ovA1 || ovB0 < ovB1;
+    const int K3 = f.K3, j3 = f.j3, s3 = f.s3, c0 = f.c0, c1 = f.c1;
+    const bool p3_active = f.p3_active != 0;
+    int iter, status = 0;
+    bool checked = false;
+    for (iter = 1; iter <= st.max_iter; iter++) {
+      const bool can_check = st.check_termination && (iter % st.check_termination == 0);
+#ifdef SCO_TIMING
+      long long tph = clock64();
+#endif
+      // ---- P1: row weights w = rho z - y ; slack elimination (registers -> wl / wp)
+      if (ROLE == 1 && act) {
+        W_wl[id] = rr * z - y;
+      } else if (ROLE == 2 && act) {
+        const double wpen = rr * z - y;
+        const double kr = kd * rr;
+        const double r1 = sigma * s1 - cd1 + kd * sl1 * wpen + bs1 * (rs1 * zs1 - ys1);
+        if (eq) {
+          const double r2 = sigma * s2 - cd2 + kd * sl2 * wpen + bs2 * (rs2 * zs2 - ys2);
+          g1 = mi11 * r1 + mi12 * r2;
+          g2 = mi12 * r1 + mi22 * r2;
+          W_wp[id] = kd * wpen - kr * (sl1 * g1 + sl2 * g2);
+        } else {
+          g1 = mi11 * r1;
+          W_wp[id] = kd * wpen - kr * sl1 * g1;
+        }
+      }
+      sync();
+      SCO_PH(0)
+      // ---- P2: reduced right-hand side (variables)
+      if (ROLE == 0 && act) {
+        double acc = 0.0, accp = 0.0;
+#pragma unroll
+        for (int k = 0; k < SCO_EH; k++) {
+          acc = fma(ec[k], sco_smem[ea[k]], acc);
+          accp = fma(ec[SCO_EH + k], sco_smem[ea[SCO_EH + k]], accp);
+        }
+        if (overflow) {
+          acc = fast_overflow(0, ovA0, ovA1, 0, acc);
+          accp = fast_overflow(1, ovB0, ovB1, 0, accp);
+        }
+        if (m_nl) acc += accp;
+        W_xt[id] = sigma * x - qh + bx * (rb * zb - yb) + acc;
+      }
+      sync();
+      SCO_PH(1)
+      // ---- P3: partial sums of x~ = S^-1 rhs (every thread of the team, whatever its role)
+      if (p3_active) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int cc = c0;
+#pragma unroll 2
+        for (; cc + 3 < c1; cc += 4) {
+          const double q0 = W_Sm[cc * n + j3], q1 = W_Sm[(cc + 1) * n + j3], q2 = W_Sm[(cc + 2) * n + j3], q3 = W_Sm[(cc + 3) * n + j3];
+          const double2 x01 = W_xt.v2(cc >> 1), x23 = W_xt.v2((cc >> 1) + 1);  // c0 is a multiple of 4
+          a0 = fma(q0, x01.x, a0);
+          a1 = fma(q1, x01.y, a1);
+          a2 = fma(q2, x23.x, a2);
+          a3 = fma(q3, x23.y, a3);
+        }
+        for (; cc < c1; cc++) a0 = fma(W_Sm[cc * n + j3], W_xt[cc], a0);
+        W_ps[s3 * n + j3] = (a0 + a2) + (a1 + a3);
+      }
+      sync();
+      SCO_PH(2)
+      // ---- P4a: x~, x and the box rows (variables)
+      if (ROLE == 0 && act) {
+        double xtil = W_ps[id];
+        for (int k = 1; k < K3; k++) xtil += W_ps[k * n + id];
+        W_xt2[id] = xtil;
+        const double xo = x;
+        const double xn = alpha * xtil + oma * xo;
+        x = xn;
+        const double zt = bx * xtil;
+        const double vv = alpha * zt + oma * zb;
+        const double zn = clampd(vv + yb * rbi, lb, ub);
+        const double dy = rb * (vv - zn);
+        yb += dy;
+        zb = zn;
+        if (can_check) { W_dxv[id] = xn - xo; W_dyb[id] = dy; }
+      }
+      sync();
+      // ---- P4b: rows
+      if ((ROLE == 1 || ROLE == 2) && act) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < SCO_EN; k++) t = fma(ec[k], sco_smem[ea[k]], t);
+        if (overflow) t = fast_overflow(ROLE == 1 ? 2 : 3, ovA0, ovA1, ovC, t);
+        double zt = t;
+        if (ROLE == 2) {
+          {
+            const double stil = g1 - hs1 * t;
+            zt += sl1 * stil;
+            const double so_ = s1;
+            const double sn = alpha * stil + oma * so_;
+            s1 = sn;
+            const double zts = bs1 * stil;
+            const double vs = alpha * zts + oma * zs1;
+            const double zns = clampd(vs + ys1 * rsi1, 0.0, us1);
+            const double dys = rs1 * (vs - zns);
+            ys1 += dys;
+            zs1 = zns;
+            if (can_check) { W_dss[id] = sn - so_; W_dys[id] = dys; }
+          }
+          if (eq) {
+            const double stil = g2 - hs2 * t;
+            zt += sl2 * stil;
+            const double so_ = s2;
+            const double sn = alpha * stil + oma * so_;
+            s2 = sn;
+            const double zts = bs2 * stil;
+            const double vs = alpha * zts + oma * zs2;
+            const double zns = clampd(vs + ys2 * rsi2, 0.0, us2);
+            const double dys = rs2 * (vs - zns);
+            ys2 += dys;
+            zs2 = zns;
+            if (can_check) { W_dss[ms + id] = sn - so_; W_dys[ms + id] = dys; }
+          }
+        }
+        const double vv = alpha * zt + oma * z;
+        const double zn = clampd(vv + y * rri, lo, hi);
+        const double dy = rr * (vv - zn);
+        y += dy;
+        z = zn;
+        if (can_check) {
+          if (ROLE == 1) W_dyl[id] = dy;
+          else W_dyp[id] = dy;
+        }
+      }
+      SCO_PH(3)
+      checked = false;
+      if (can_check || iter == st.max_iter) {
+        // iterates -> the shared-memory arrays check() / the certificates / the epilogue work on
+        if (act) {
+          if (ROLE == 0) { W_x[id] = x; W_zb[id] = zb; W_yb[id] = yb; }
+          else if (ROLE == 1) { W_zl[id] = z; W_yl[id] = y; }
+          else if (ROLE == 2) {
+            W_zp[id] = z; W_yp[id] = y;
+            W_s[id] = s1; W_zs[id] = zs1; W_ys[id] = ys1;
+            if (eq) { W_s[ms + id] = s2; W_zs[ms + id] = zs2; W_ys[ms + id] = ys2; }
+          }
+        }
+        sync();
+        if (can_check) {
+          status = check(0, res.pri_res, res.dua_res, nullptr);
+          checked = true;
+          if (status != 0) break;
+          sync();
+        }
+      }
+      SCO_PH(4)
+    }
+    iter_out = iter;
+    checked_out = checked;
+    return status;
+  }
+
+  // roles start on warp boundaries: ceil32(n) variable lanes, ceil32(m_lin) linear-row lanes, ceil32(m_nl) penalty-row lanes
+  __device__ __forceinline__ bool fast_fits() const {
+    return ((n + 31) & ~31) + ((m_lin + 31) & ~31) + ((m_nl + 31) & ~31) <= TEAM;
+  }
+
+  __device__ __noinline__ int fast_loop(int &iter_out, bool &checked_out, QPResult &res) {
+    const int n = this->n, m_lin = this->m_lin, m_nl = this->m_nl, tid = this->tid;
+    const QPW &wq = this->w;
+    const int nV = (n + 31) & ~31, nL = (m_lin + 31) & ~31, nP = (m_nl + 31) & ~31;
+    FastCtx f;
+    const int role = tid < nV ? 0 : tid < nV + nL ? 1 : tid < nV + nL + nP ? 2 : 3;
+    f.id = role == 0 ? tid : role == 1 ? tid - nV : tid - nV - nL;
+    f.act = role == 0 ? f.id < n : role == 1 ? f.id < m_lin : role == 2 ? f.id < m_nl : 0;
+    // S^-1 rhs: thread (j3, s3) sums the columns [c0, c1) of row j3 (S^-1 is symmetric: column access)
+    f.K3 = (TEAM / n) < 4 ? (TEAM / n) : 4;
+    f.j3 = tid % n;
+    f.s3 = tid / n;
+    const int CS = ((n + f.K3 - 1) / f.K3 + 3) & ~3;
+    f.c0 = f.s3 * CS;
+    f.c1 = (f.s3 + 1) * CS < n ? (f.s3 + 1) * CS : n;
+    f.p3_active = f.s3 < f.K3 && f.c0 < n;
+    for (int e = tid; e < f.K3 * n; e += TEAM) wq.ps[e] = 0.0;  // segments beyond n contribute exact zeros
+    sync();
+    if (role == 0) return fast_role<0>(f, iter_out, checked_out, res);
+    if (role == 1) return fast_role<1>(f, iter_out, checked_out, res);
+    if (role == 2) return fast_role<2>(f, iter_out, checked_out, res);
+    return fast_role<3>(f, iter_out, checked_out, res);
+  }
+
   // ================================================================== the ADMM loop
   // On return W_x (user variables) and W_s (slacks) hold the UNSCALED solution.
   // generic shared-memory ADMM loop; returns the status (0 = max_iter reached without a verdict)
@@ -591,9 +909,6 @@ struct QPSolver {
       const bool want_delta = can_check || do_rho;
 #ifdef SCO_TIMING
       long long tph = clock64();
-#define SCO_PH(k) { sync(); const long long tq_ = clock64(); res.cyc_c[k] += tq_ - tph; tph = tq_; }
-#else
-#define SCO_PH(k)
 #endif
       // ---- P1: row weights  w = rho z - y, slack elimination
       for (int r = tid; r < m_lin; r += TEAM) W_wl[r] = W_rl[r] * W_zl[r] - W_yl[r];
@@ -737,6 +1052,9 @@ struct QPSolver {
     const long long t_begin = clock64();
 #endif
     load_and_scale();
+#ifdef SCO_TIMING
+    const long long t_scaled = clock64();
+#endif
     rho = st.rho;
     set_rho();
     assemble_and_invert(false);
@@ -746,11 +1064,15 @@ struct QPSolver {
     res.cyc_check = 0;
     for (int k = 0; k < 5; k++) res.cyc_c[k] = 0;
     res.cyc_setup = clock64() - t_begin;
+    res.cyc_scale = t_scaled - t_begin;
     const long long t_loop = clock64();
 #endif
     int iter = 0, status = 0;
     bool checked = false;
-    status = generic_loop(iter, checked, res);
+    // one thread per entity when the team is large enough (sco_create sizes it so); adaptive rho re-factorises
+    // inside the loop and stays on the shared-memory loop
+    if (fast_fits() && !st.adaptive_rho && !st.force_generic) status = fast_loop(iter, checked, res);
+    else status = generic_loop(iter, checked, res);
 #ifdef SCO_TIMING
     res.cyc_loop = clock64() - t_loop;
 #endif

@@ -312,3 +312,25 @@ def test_bad_processing_order_is_refused(engines):
     good = eng.solve_batch(params[:B], x0[:B], _settings(), order=torch.arange(B - 1, -1, -1, dtype=torch.int32))
     ref = eng.solve_batch(params[:B], x0[:B], _settings())
     assert np.array_equal(good["x"].cpu().numpy(), ref["x"].cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["point_robot", "arm", "qcqp"])
+def test_thread_per_entity_loop_matches_the_strided_loop(engines, name):
+    """sco_qp.cuh: fast_loop (one thread per variable / row, iterates and constants in registers) against
+    generic_loop (the round-1 shared-memory loop, force_generic = 1) on the same QPs: same status, same iteration
+    count, x to 1e-9 -- for penalty QPs and for the closest-point projection."""
+    eng, st, params, x0 = engines[name]
+    B = STAGE_N[name]
+    params, x0 = params[:B], x0[:B]
+    f, J, b, _ = eng.convexify(params, x0)
+    for kdup, pi, delta in [(1, 1.0, 1.0), (3, 10.0, 0.1), (6, 1e3, 3e-5)]:
+        kw = dict(J=J, b=b, lbx=x0 - delta, ubx=x0 + delta, pi=np.full(B, pi), kdup=np.full(B, kdup, np.int32))
+        xa, sa, ia = eng.qp_solve(params, _settings(), **kw)
+        xb, sb, ib = eng.qp_solve(params, _settings(force_generic=1), **kw)
+        assert np.array_equal(sa.cpu().numpy(), sb.cpu().numpy()), (name, kdup)
+        assert np.array_equal(ia.cpu().numpy(), ib.cpu().numpy()), (name, kdup, ia.cpu().numpy(), ib.cpu().numpy())
+        assert np.abs(xa.cpu().numpy() - xb.cpu().numpy()).max() <= 1e-9, (name, kdup)
+    xa, sa, ia = eng.qp_solve(params, _settings(), xref=x0, use_penalty=False, closest_point=True)
+    xb, sb, ib = eng.qp_solve(params, _settings(force_generic=1), xref=x0, use_penalty=False, closest_point=True)
+    assert np.array_equal(sa.cpu().numpy(), sb.cpu().numpy()) and np.array_equal(ia.cpu().numpy(), ib.cpu().numpy())
+    assert np.abs(xa.cpu().numpy() - xb.cpu().numpy()).max() <= 1e-9
