@@ -628,24 +628,66 @@ struct QPSolver {
   // Requires ceil32(n) + ceil32(m_lin) + ceil32(m_nl) <= TEAM and no adaptive rho.
 #define SCO_EN 6
 #define SCO_EH 3
+  // Everything the hot loop needs, by value: a handful of shared-memory offsets and scalars.  The loop must not touch
+  // the solver object (QPW offsets, settings, index arrays live in local memory: with 512 threads per team and
+  // ~150 KB of shared memory the L1 that backs local memory is a few dozen KB, and every such access is an L2 round
+  // trip -- measured: 1,500 cycles for a phase that does one multiply-add).
   struct FastCtx {
     int id;        // index of the entity inside its role
     int act;       // 0: padding lane of a role's last warp
+    int n, ms;
     int K3, j3, s3, c0, c1, p3_active;  // S^-1 rhs: column segment [c0, c1) of row j3
+    int o_Sm, o_xt, o_xt2, o_ps, o_wl, o_wp;  // shared-memory offsets (doubles)
+    int max_iter, chk, has_pen;
+    double sigma, alpha, kd, cpi;
   };
+
+  // Hand-over of the iterates (and, at a test iteration, of the last step's deltas) to the shared-memory arrays that
+  // check() / the certificates / the epilogue of solve() work on, followed by the termination test.  Out of line: the
+  // ~20 array offsets it needs are loaded here, once per check_termination iterations, not carried through the loop.
+  //   ROLE 0: v = x zb yb, d = dx dyb          ROLE 1: v = z y, d = dy
+  //   ROLE 2: v = zp yp s1 zs1 ys1 s2 zs2 ys2, d = dyp dss1 dys1 dss2 dys2
+  template <int ROLE>
+  __device__ __noinline__ int fast_flush(int id, int act, int eq, int can_check, QPResult &res, double v0, double v1,
+                                         double v2, double v3, double v4, double v5, double v6, double v7, double d0,
+                                         double d1, double d2, double d3, double d4) {
+    const QPW &wq = this->w;
+    const int ms = this->ms;
+    if (act) {
+      if (ROLE == 0) {
+        wq.x[id] = v0; wq.zb[id] = v1; wq.yb[id] = v2;
+        if (can_check) { wq.dxv[id] = d0; wq.dyb[id] = d1; }
+      } else if (ROLE == 1) {
+        wq.zl[id] = v0; wq.yl[id] = v1;
+        if (can_check) wq.dyl[id] = d0;
+      } else if (ROLE == 2) {
+        wq.zp[id] = v0; wq.yp[id] = v1;
+        wq.s[id] = v2; wq.zs[id] = v3; wq.ys[id] = v4;
+        if (eq) { wq.s[ms + id] = v5; wq.zs[ms + id] = v6; wq.ys[ms + id] = v7; }
+        if (can_check) {
+          wq.dyp[id] = d0; wq.dss[id] = d1; wq.dys[id] = d2;
+          if (eq) { wq.dss[ms + id] = d3; wq.dys[ms + id] = d4; }
+        }
+      }
+    }
+    sync();
+    int status = 0;
+    if (can_check) {
+      status = check(0, res.pri_res, res.dua_res, nullptr);
+      if (status == 0) sync();
+    }
+    return status;
+  }
 
   template <int ROLE>  // 0 variable, 1 linear row, 2 penalty row, 3 none (idle warps still do their share of S^-1 rhs)
   __device__ __noinline__ int fast_role(const FastCtx f, int &iter_out, bool &checked_out, QPResult &res) {
-    SCO_QP_LOCALS
-    const double sigma = st.sigma, alpha = st.alpha, oma = 1.0 - st.alpha;
-    const double kd = a.kd;
-    const int id = f.id;
+    const int id = f.id, n = f.n;
     const bool act = f.act != 0;
-    // ---- entries.  Unused slots multiply the coefficient 0 with W_ps[0], which always holds a finite number.
+    // ---- entries.  Unused slots multiply the coefficient 0 with ps[0], which always holds a finite number.
     double ec[SCO_EN];
     int ea[SCO_EN];
 #pragma unroll
-    for (int k = 0; k < SCO_EN; k++) { ec[k] = 0.0; ea[k] = W_ps.off; }
+    for (int k = 0; k < SCO_EN; k++) { ec[k] = 0.0; ea[k] = f.o_ps; }
     int ovA0 = 0, ovA1 = 0, ovB0 = 0, ovB1 = 0, ovC = 0;  // entries beyond the register slots (rare)
     // ---- state and constants of the entity
     double x = 0.0, zb = 0.0, yb = 0.0, qh = 0.0, bx = 0.0, rb = 1.0, rbi = 1.0, lb = 0.0, ub = 0.0;   // variable
@@ -653,63 +695,73 @@ struct QPSolver {
     double mi11 = 0.0, mi12 = 0.0, mi22 = 0.0;                                                          // pen
     double s1 = 0.0, zs1 = 0.0, ys1 = 0.0, sl1 = 0.0, bs1 = 0.0, rs1 = 1.0, rsi1 = 1.0, cd1 = 0.0, us1 = 0.0, hs1 = 0.0, g1 = 0.0;
     double s2 = 0.0, zs2 = 0.0, ys2 = 0.0, sl2 = 0.0, bs2 = 0.0, rs2 = 1.0, rsi2 = 1.0, cd2 = 0.0, us2 = 0.0, hs2 = 0.0, g2 = 0.0;
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, d4 = 0.0;  // deltas of the last iteration (certificates)
     int eq = 0;
-    if (ROLE == 0 && act) {
-      const int j = id;
-      qh = W_qh[j]; bx = W_bx[j]; rb = W_rb[j]; rbi = 1.0 / rb; lb = W_lb[j]; ub = W_ub[j];
-      int pl0 = 0, pl1 = 0, pp0 = 0, pp1 = 0;
-      if (m_lin) { pl0 = __ldg(S.lin_cptr + j); pl1 = __ldg(S.lin_cptr + j + 1); }
-      if (m_nl) { pp0 = __ldg(S.pc_ptr + j); pp1 = __ldg(S.pc_ptr + j + 1); }
+    {
+      // one-time loads through the solver object (see FastCtx)
+      const QPW &wq = this->w;
+      const DevStruct &SS = this->S;
+      const int m_lin = this->m_lin, m_nl = this->m_nl, ms = f.ms;
+      if (ROLE == 0 && act) {
+        const int j = id;
+        qh = wq.qh[j]; bx = wq.bx[j]; rb = wq.rb[j]; rbi = 1.0 / rb; lb = wq.lb[j]; ub = wq.ub[j];
+        int pl0 = 0, pl1 = 0, pp0 = 0, pp1 = 0;
+        if (m_lin) { pl0 = __ldg(SS.lin_cptr + j); pl1 = __ldg(SS.lin_cptr + j + 1); }
+        if (m_nl) { pp0 = __ldg(SS.pc_ptr + j); pp1 = __ldg(SS.pc_ptr + j + 1); }
 #pragma unroll
-      for (int k = 0; k < SCO_EH; k++) {
-        if (pl0 + k < pl1) {
-          ec[k] = W_Als[__ldg(S.lin_centry + pl0 + k)];
-          ea[k] = W_wl.off + __ldg(S.lin_crow + pl0 + k);
+        for (int k = 0; k < SCO_EH; k++) {
+          if (pl0 + k < pl1) {
+            ec[k] = wq.Als[__ldg(SS.lin_centry + pl0 + k)];
+            ea[k] = f.o_wl + __ldg(SS.lin_crow + pl0 + k);
+          }
+          if (pp0 + k < pp1) {
+            ec[SCO_EH + k] = wq.Js[__ldg(SS.pc_e + pp0 + k)];
+            ea[SCO_EH + k] = f.o_wp + __ldg(SS.pc_r + pp0 + k);
+          }
         }
-        if (pp0 + k < pp1) {
-          ec[SCO_EH + k] = W_Js[__ldg(S.pc_e + pp0 + k)];
-          ea[SCO_EH + k] = W_wp.off + __ldg(S.pc_r + pp0 + k);
+        ovA0 = pl0 + SCO_EH; ovA1 = pl1; ovB0 = pp0 + SCO_EH; ovB1 = pp1;
+      } else if (ROLE == 1 && act) {
+        const int r = id;
+        rr = wq.rl[r]; rri = 1.0 / rr; lo = wq.ll[r]; hi = wq.ul[r];
+        const int p0 = __ldg(SS.lin_rowptr + r), p1 = __ldg(SS.lin_rowptr + r + 1);
+#pragma unroll
+        for (int k = 0; k < SCO_EN; k++)
+          if (p0 + k < p1) { ec[k] = wq.Als[p0 + k]; ea[k] = f.o_xt2 + __ldg(SS.lin_col + p0 + k); }
+        ovA0 = p0 + SCO_EN; ovA1 = p1;
+      } else if (ROLE == 2 && act) {
+        const int i = id;
+        eq = __ldg(SS.row_eq + i);
+        rr = wq.rp[i]; rri = 1.0 / rr; lo = wq.lp[i]; hi = wq.up[i];
+        mi11 = wq.Minv[3 * i]; mi12 = wq.Minv[3 * i + 1]; mi22 = wq.Minv[3 * i + 2];
+        sl1 = wq.sl[i]; bs1 = wq.bs[i]; rs1 = wq.rs[i]; rsi1 = 1.0 / rs1; cd1 = f.cpi * wq.Ds[i]; us1 = OSQP_INFTY * wq.Es[i]; hs1 = wq.hs[i];
+        if (eq) {
+          const int i2 = ms + i;
+          sl2 = wq.sl[i2]; bs2 = wq.bs[i2]; rs2 = wq.rs[i2]; rsi2 = 1.0 / rs2; cd2 = f.cpi * wq.Ds[i2]; us2 = OSQP_INFTY * wq.Es[i2]; hs2 = wq.hs[i2];
         }
-      }
-      ovA0 = pl0 + SCO_EH; ovA1 = pl1; ovB0 = pp0 + SCO_EH; ovB1 = pp1;
-    } else if (ROLE == 1 && act) {
-      const int r = id;
-      rr = W_rl[r]; rri = 1.0 / rr; lo = W_ll[r]; hi = W_ul[r];
-      const int p0 = __ldg(S.lin_rowptr + r), p1 = __ldg(S.lin_rowptr + r + 1);
+        const int so = __ldg(SS.row_soff + i), go = __ldg(SS.row_goff + i), wd = __ldg(SS.row_w + i);
 #pragma unroll
-      for (int k = 0; k < SCO_EN; k++)
-        if (p0 + k < p1) { ec[k] = W_Als[p0 + k]; ea[k] = W_xt2.off + __ldg(S.lin_col + p0 + k); }
-      ovA0 = p0 + SCO_EN; ovA1 = p1;
-    } else if (ROLE == 2 && act) {
-      const int i = id;
-      const double cpi = c * a.pi;
-      eq = __ldg(S.row_eq + i);
-      rr = W_rp[i]; rri = 1.0 / rr; lo = W_lp[i]; hi = W_up[i];
-      mi11 = W_Minv[3 * i]; mi12 = W_Minv[3 * i + 1]; mi22 = W_Minv[3 * i + 2];
-      sl1 = W_sl[i]; bs1 = W_bs[i]; rs1 = W_rs[i]; rsi1 = 1.0 / rs1; cd1 = cpi * W_Ds[i]; us1 = OSQP_INFTY * W_Es[i]; hs1 = W_hs[i];
-      if (eq) {
-        const int i2 = ms + i;
-        sl2 = W_sl[i2]; bs2 = W_bs[i2]; rs2 = W_rs[i2]; rsi2 = 1.0 / rs2; cd2 = cpi * W_Ds[i2]; us2 = OSQP_INFTY * W_Es[i2]; hs2 = W_hs[i2];
+        for (int k = 0; k < SCO_EN; k++)
+          if (k < wd) { ec[k] = wq.Js[so + k]; ea[k] = f.o_xt2 + __ldg(SS.jcol_g + go + k); }
+        ovA0 = so + SCO_EN; ovA1 = so + wd; ovC = go - so;  // overflow: Js[p], column jcol_g[p + ovC]
       }
-      const int so = __ldg(S.row_soff + i), go = __ldg(S.row_goff + i), wd = __ldg(S.row_w + i);
-#pragma unroll
-      for (int k = 0; k < SCO_EN; k++)
-        if (k < wd) { ec[k] = W_Js[so + k]; ea[k] = W_xt2.off + __ldg(S.jcol_g + go + k); }
-      ovA0 = so + SCO_EN; ovA1 = so + wd; ovC = go - so;  // overflow: W_Js[p], column jcol_g[p + ovC]
     }
     const bool overflow = ovA0 < ovA1 || ovB0 < ovB1;
+    const double sigma = f.sigma, alpha = f.alpha, oma = 1.0 - f.alpha, kd = f.kd;
     const int K3 = f.K3, j3 = f.j3, s3 = f.s3, c0 = f.c0, c1 = f.c1;
     const bool p3_active = f.p3_active != 0;
-    int iter, status = 0;
+    const int o_Sm = f.o_Sm, o_xt = f.o_xt, o_xt2 = f.o_xt2, o_ps = f.o_ps, o_wl = f.o_wl, o_wp = f.o_wp;
+    const int max_iter = f.max_iter, chk = f.chk;
+    int iter, status = 0, next_check = chk ? chk : max_iter + 1;
     bool checked = false;
-    for (iter = 1; iter <= st.max_iter; iter++) {
-      const bool can_check = st.check_termination && (iter % st.check_termination == 0);
+    for (iter = 1; iter <= max_iter; iter++) {
+      const bool can_check = iter == next_check;
+      if (can_check) next_check += chk;
 #ifdef SCO_TIMING
       long long tph = clock64();
 #endif
       // ---- P1: row weights w = rho z - y ; slack elimination (registers -> wl / wp)
       if (ROLE == 1 && act) {
-        W_wl[id] = rr * z - y;
+        sco_smem[o_wl + id] = rr * z - y;
       } else if (ROLE == 2 && act) {
         const double wpen = rr * z - y;
         const double kr = kd * rr;
@@ -718,10 +770,10 @@ struct QPSolver {
           const double r2 = sigma * s2 - cd2 + kd * sl2 * wpen + bs2 * (rs2 * zs2 - ys2);
           g1 = mi11 * r1 + mi12 * r2;
           g2 = mi12 * r1 + mi22 * r2;
-          W_wp[id] = kd * wpen - kr * (sl1 * g1 + sl2 * g2);
+          sco_smem[o_wp + id] = kd * wpen - kr * (sl1 * g1 + sl2 * g2);
         } else {
           g1 = mi11 * r1;
-          W_wp[id] = kd * wpen - kr * sl1 * g1;
+          sco_smem[o_wp + id] = kd * wpen - kr * sl1 * g1;
         }
       }
       sync();
@@ -738,8 +790,8 @@ struct QPSolver {
           acc = fast_overflow(0, ovA0, ovA1, 0, acc);
           accp = fast_overflow(1, ovB0, ovB1, 0, accp);
         }
-        if (m_nl) acc += accp;
-        W_xt[id] = sigma * x - qh + bx * (rb * zb - yb) + acc;
+        if (f.has_pen) acc += accp;
+        sco_smem[o_xt + id] = sigma * x - qh + bx * (rb * zb - yb) + acc;
       }
       sync();
       SCO_PH(1)
@@ -747,25 +799,27 @@ struct QPSolver {
       if (p3_active) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int cc = c0;
+        const double *Sc = sco_smem + o_Sm + j3;
+        const double2 *xv = sco_smem2 + (o_xt >> 1);
 #pragma unroll 2
         for (; cc + 3 < c1; cc += 4) {
-          const double q0 = W_Sm[cc * n + j3], q1 = W_Sm[(cc + 1) * n + j3], q2 = W_Sm[(cc + 2) * n + j3], q3 = W_Sm[(cc + 3) * n + j3];
-          const double2 x01 = W_xt.v2(cc >> 1), x23 = W_xt.v2((cc >> 1) + 1);  // c0 is a multiple of 4
+          const double q0 = Sc[cc * n], q1 = Sc[(cc + 1) * n], q2 = Sc[(cc + 2) * n], q3 = Sc[(cc + 3) * n];
+          const double2 x01 = xv[cc >> 1], x23 = xv[(cc >> 1) + 1];  // c0 is a multiple of 4
           a0 = fma(q0, x01.x, a0);
           a1 = fma(q1, x01.y, a1);
           a2 = fma(q2, x23.x, a2);
           a3 = fma(q3, x23.y, a3);
         }
-        for (; cc < c1; cc++) a0 = fma(W_Sm[cc * n + j3], W_xt[cc], a0);
-        W_ps[s3 * n + j3] = (a0 + a2) + (a1 + a3);
+        for (; cc < c1; cc++) a0 = fma(Sc[cc * n], sco_smem[o_xt + cc], a0);
+        sco_smem[o_ps + s3 * n + j3] = (a0 + a2) + (a1 + a3);
       }
       sync();
       SCO_PH(2)
       // ---- P4a: x~, x and the box rows (variables)
       if (ROLE == 0 && act) {
-        double xtil = W_ps[id];
-        for (int k = 1; k < K3; k++) xtil += W_ps[k * n + id];
-        W_xt2[id] = xtil;
+        double xtil = sco_smem[o_ps + id];
+        for (int k = 1; k < K3; k++) xtil += sco_smem[o_ps + k * n + id];
+        sco_smem[o_xt2 + id] = xtil;
         const double xo = x;
         const double xn = alpha * xtil + oma * xo;
         x = xn;
@@ -775,7 +829,7 @@ struct QPSolver {
         const double dy = rb * (vv - zn);
         yb += dy;
         zb = zn;
-        if (can_check) { W_dxv[id] = xn - xo; W_dyb[id] = dy; }
+        d0 = xn - xo; d1 = dy;
       }
       sync();
       // ---- P4b: rows
@@ -798,7 +852,7 @@ struct QPSolver {
             const double dys = rs1 * (vs - zns);
             ys1 += dys;
             zs1 = zns;
-            if (can_check) { W_dss[id] = sn - so_; W_dys[id] = dys; }
+            d1 = sn - so_; d2 = dys;
           }
           if (eq) {
             const double stil = g2 - hs2 * t;
@@ -812,7 +866,7 @@ struct QPSolver {
             const double dys = rs2 * (vs - zns);
             ys2 += dys;
             zs2 = zns;
-            if (can_check) { W_dss[ms + id] = sn - so_; W_dys[ms + id] = dys; }
+            d3 = sn - so_; d4 = dys;
           }
         }
         const double vv = alpha * zt + oma * z;
@@ -820,31 +874,17 @@ struct QPSolver {
         const double dy = rr * (vv - zn);
         y += dy;
         z = zn;
-        if (can_check) {
-          if (ROLE == 1) W_dyl[id] = dy;
-          else W_dyp[id] = dy;
-        }
+        d0 = dy;
       }
       SCO_PH(3)
       checked = false;
-      if (can_check || iter == st.max_iter) {
-        // iterates -> the shared-memory arrays check() / the certificates / the epilogue work on
-        if (act) {
-          if (ROLE == 0) { W_x[id] = x; W_zb[id] = zb; W_yb[id] = yb; }
-          else if (ROLE == 1) { W_zl[id] = z; W_yl[id] = y; }
-          else if (ROLE == 2) {
-            W_zp[id] = z; W_yp[id] = y;
-            W_s[id] = s1; W_zs[id] = zs1; W_ys[id] = ys1;
-            if (eq) { W_s[ms + id] = s2; W_zs[ms + id] = zs2; W_ys[ms + id] = ys2; }
-          }
-        }
-        sync();
-        if (can_check) {
-          status = check(0, res.pri_res, res.dua_res, nullptr);
-          checked = true;
-          if (status != 0) break;
-          sync();
-        }
+      if (can_check || iter == max_iter) {
+        if (ROLE == 0) status = fast_flush<0>(id, act, 0, can_check, res, x, zb, yb, 0, 0, 0, 0, 0, d0, d1, 0, 0, 0);
+        else if (ROLE == 1) status = fast_flush<1>(id, act, 0, can_check, res, z, y, 0, 0, 0, 0, 0, 0, d0, 0, 0, 0, 0);
+        else if (ROLE == 2) status = fast_flush<2>(id, act, eq, can_check, res, z, y, s1, zs1, ys1, s2, zs2, ys2, d0, d1, d2, d3, d4);
+        else status = fast_flush<3>(id, 0, 0, can_check, res, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+        checked = can_check;
+        if (status != 0) break;
       }
       SCO_PH(4)
     }
@@ -866,6 +906,7 @@ struct QPSolver {
     const int role = tid < nV ? 0 : tid < nV + nL ? 1 : tid < nV + nL + nP ? 2 : 3;
     f.id = role == 0 ? tid : role == 1 ? tid - nV : tid - nV - nL;
     f.act = role == 0 ? f.id < n : role == 1 ? f.id < m_lin : role == 2 ? f.id < m_nl : 0;
+    f.n = n; f.ms = this->ms;
     // S^-1 rhs: thread (j3, s3) sums the columns [c0, c1) of row j3 (S^-1 is symmetric: column access)
     f.K3 = (TEAM / n) < 4 ? (TEAM / n) : 4;
     f.j3 = tid % n;
@@ -874,6 +915,9 @@ struct QPSolver {
     f.c0 = f.s3 * CS;
     f.c1 = (f.s3 + 1) * CS < n ? (f.s3 + 1) * CS : n;
     f.p3_active = f.s3 < f.K3 && f.c0 < n;
+    f.o_Sm = wq.Sm.off; f.o_xt = wq.xt.off; f.o_xt2 = wq.xt2.off; f.o_ps = wq.ps.off; f.o_wl = wq.wl.off; f.o_wp = wq.wp.off;
+    f.max_iter = this->st.max_iter; f.chk = this->st.check_termination; f.has_pen = m_nl != 0;
+    f.sigma = this->st.sigma; f.alpha = this->st.alpha; f.kd = this->a.kd; f.cpi = this->c * this->a.pi;
     for (int e = tid; e < f.K3 * n; e += TEAM) wq.ps[e] = 0.0;  // segments beyond n contribute exact zeros
     sync();
     if (role == 0) return fast_role<0>(f, iter_out, checked_out, res);
