@@ -22,9 +22,9 @@ for force in (1, 0):
     torch.cuda.synchronize()
     xq = xq.cpu().numpy(); it = iters.cpu().numpy().astype(float)
     res[force] = (status.cpu().numpy(), it)
-    loop, setup, scale = xq[:, 0], xq[:, 2], xq[:, 8]
+    loop, setup, scale, chk = xq[:, 0], xq[:, 2], xq[:, 8], xq[:, 1]
     ph = [xq[:, 3 + k] for k in range(5)]
-    print("%s B=%d team %d ctas/sm %d %s: iters mean %.0f | cycles/iter %.0f | setup %.0f (load + Ruiz %.0f, S + inverse %.0f) | per iteration: P1 %.0f P2 %.0f P3 %.0f P4 %.0f tests+rest %.0f" % (
+    print("%s B=%d team %d ctas/sm %d %s: iters mean %.0f | cycles/iter %.0f | setup %.0f (load + Ruiz %.0f, S + inverse %.0f) | per iteration: P1 %.0f P2 %.0f P3 %.0f P4 %.0f tests+rest %.0f (check() alone %.0f per test)" % (
         name, B, eng.team, eng.occupancy, "generic_loop" if force else "fast_loop", it.mean(), (loop / it).mean(), setup.mean(), scale.mean(),
-        (setup - scale).mean(), *[(p / it).mean() for p in ph]))
+        (setup - scale).mean(), *[(p / it).mean() for p in ph], (chk / np.maximum(it // 25, 1)).mean()))
 print("same status:", bool((res[0][0] == res[1][0]).all()), " same iteration counts:", bool((res[0][1] == res[1][1]).all()))

@@ -108,7 +108,7 @@ static void build_layout(DevStruct &S, int team) {
   L.s = take(sl); L.Ds = take(sl); L.sl = take(sl); L.bs = take(sl); L.zs = take(sl); L.ys = take(sl);
   L.Es = take(sl); L.gs = take(sl); L.hs = take(sl); L.rs = take(sl); L.dss = take(sl); L.dys = take(sl);
   L.Minv = take(3 * mp);
-  L.red = take(std::max(team / 32, 8) * 16);
+  L.red = take((std::max(team / 32, 8) + 1) * 16);  // one 16-double slot per warp + one for the combined results
   L.msk = take((mp + 1) / 2);
   L.stage = take(std::max((team / 32) * S.stage_per_warp, 100));
   L.Hq = take(S.obj_len ? n * n + 2 : 0); L.gq = take(S.obj_len ? n : 0);
@@ -373,6 +373,13 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
       }
     if (S.obj_len) bw = n - 1;  // the degree-2 model of a non-quadratic objective is dense
     S.s_bw = std::min(bw, n - 1);
+    // thread-per-entity ADMM loop (sco_qp.cuh: fast_role keeps SCO_EN = 8 row entries / SCO_EH = 4 + 4 column entries
+    // in registers and has no path for more)
+    bool ok = true;
+    for (int r = 0; r < desc->m_lin; r++) ok = ok && lrp[r + 1] - lrp[r] <= 8;
+    for (int i = 0; i < m_nl; i++) ok = ok && row_w[i] <= 8;
+    for (int j = 0; j < n; j++) ok = ok && lcptr[j + 1] - lcptr[j] <= 4 && pc_ptr[j + 1] - pc_ptr[j] <= 4;
+    S.fast_ok = ok ? 1 : 0;
   }
   if (rc) { sco_destroy(h); return SCO_ERR_CUDA; }
   // ---- dense fast path: one dense hinge block, no linear rows, sizes within the instantiated table

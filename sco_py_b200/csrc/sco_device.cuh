@@ -94,6 +94,7 @@ struct DevStruct {
   int n, m_lin, nnz_lin, n_blocks, n_groups, m_nl, n_slack, jnnz, n_q, nsl;
   int sjnnz;           // padded Jacobian entries in shared memory
   int dense_kind;      // != 0: two-warp dense solve (sco_dense.cuh), index into its size table
+  int fast_ok;         // rows of A with <= 8 entries, columns with <= 4 + 4: the thread-per-entity loop applies
   int s_bw;            // structural half-bandwidth of S = P + A'RA (max |i - j| over its pattern): the Gauss-Jordan
                        // sweep of pivot k only touches the leading (k + s_bw + 1)^2 block
   int stage_per_warp;  // doubles
@@ -123,6 +124,9 @@ struct DevStruct {
   DevBlock blocks[SCO_DEV_MAX_BLOCKS];
   Layout L;
 };
+
+extern __shared__ __align__(16) double sco_smem[];
+extern __shared__ __align__(16) double2 sco_smem2[];  // same storage, viewed as 16-byte words
 
 // By-value view of the index arrays and sizes a QP needs.  Device functions copy it (and QPW,
 // DevSettings) into locals on entry: anything read through a reference lives behind a generic pointer,
@@ -157,8 +161,6 @@ __device__ __forceinline__ const double *field_ptr(const DevStruct &S, const Dev
   return f.off < 0 ? nullptr : ((f.shared ? S.shared : prm) + f.off);
 }
 
-extern __shared__ __align__(16) double sco_smem[];
-extern __shared__ __align__(16) double2 sco_smem2[];  // same storage, viewed as 16-byte words
 
 struct Sh {
   int off;
@@ -210,6 +212,43 @@ struct Team {
           acc = IS_MAX ? fmax(acc, red[ww * 16 + k]) : acc + red[ww * 16 + k];
         v[k] = acc;
       }
+    }
+  }
+  // KM maxima and KS sums in one pass (KM + KS <= 16).  The warps' partial results are combined by KM + KS threads
+  // (in warp order, like `reduce`) and read back by everybody: three barriers, but no thread walks all the warps'
+  // partials for every value (with 16 warps that walk was 16 shared loads per value per thread).
+  template <int KM, int KS>
+  static __device__ __forceinline__ void reduce_mixed(double (&vm)[KM], double (&vs)[KS], Sh red) {
+    static_assert(KM + KS <= 16, "one 16-double slot per warp");
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < KM; k++) vm[k] = fmax(vm[k], __shfl_xor_sync(0xffffffffu, vm[k], o));
+#pragma unroll
+      for (int k = 0; k < KS; k++) vs[k] += __shfl_xor_sync(0xffffffffu, vs[k], o);
+    }
+    if (TEAM > 32) {
+      constexpr int NW = TEAM / 32;
+      const int wi = threadIdx.x >> 5, l = threadIdx.x & 31;
+      __syncthreads();
+      if (l == 0) {
+#pragma unroll
+        for (int k = 0; k < KM; k++) red[wi * 16 + k] = vm[k];
+#pragma unroll
+        for (int k = 0; k < KS; k++) red[wi * 16 + KM + k] = vs[k];
+      }
+      __syncthreads();
+      if (threadIdx.x < KM + KS) {
+        const int k = threadIdx.x;
+        double acc = red[k];
+        for (int ww = 1; ww < NW; ww++) acc = k < KM ? fmax(acc, red[ww * 16 + k]) : acc + red[ww * 16 + k];
+        red[NW * 16 + k] = acc;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < KM; k++) vm[k] = red[NW * 16 + k];
+#pragma unroll
+      for (int k = 0; k < KS; k++) vs[k] = red[NW * 16 + KM + k];
     }
   }
   template <int K>

@@ -14,10 +14,12 @@
 #ifndef SCO_DK
 #define SCO_DK 0
 #endif
-#if defined(SCO_TEAM) && SCO_TEAM >= 256
+#if defined(SCO_TEAM) && SCO_TEAM >= 512
 // A warp's registers come out of its SM sub-partition's 16,384: a 512-thread team has four warps on each, so 128
-// registers per thread is its ceiling (a 448-thread team has the same problem: 4 + 4 + 3 + 3 warps); a 256-thread
-// team at 128 registers fits two teams per SM, which overlaps the barrier-bound phases of two problems.
+// registers per thread is its ceiling (a 448-thread team has the same problem: 4 + 4 + 3 + 3 warps).  A 256-thread
+// team keeps the full budget (one team per SM): at 128 registers two teams fit, but the penalty-row role spills and
+// the point robot's 1,024-problem batch -- whose step is set by one 794 k-iteration problem -- ran at 1,050
+// instead of 1,535 problems/s (profiles/r2_generic_cycles.txt).
 #define SCO_MAXNREG 128
 #else
 #define SCO_MAXNREG 255

@@ -153,8 +153,8 @@ struct QPSolver {
     double cp = 0.0;                                                                                        \
     if (a.closest) cp = W_D[j] * fabs(W_Sm[j * n + j]);                                                     \
     else if (a.has_hq) { for (int i = 0; i < n; i++) cp = fmax(cp, W_D[i] * fabs(W_Sm[i * n + j])); }       \
-    else for (int p = __ldg(S.P_cptr + j); p < __ldg(S.P_cptr + j + 1); p++) {                              \
-      const int i = __ldg(S.P_row + p);                                                                     \
+    else for (int p = __ldg(S.P_cptr + (j)); p < __ldg(S.P_cptr + (j + 1)); p++) {                              \
+      const int i = __ldg(S.P_row + (p));                                                                     \
       cp = fmax(cp, W_D[i] * fabs(W_Sm[i * n + j]));                                                        \
     }                                                                                                       \
     return cp * c * W_D[j];                                                                                 \
@@ -164,8 +164,8 @@ struct QPSolver {
     double px = 0.0;                                                                                        \
     if (a.closest) px = 2.0 * v[j];                                                                         \
     else if (a.has_hq) { for (int k = 0; k < n; k++) px += psym(k, j) * v[k]; }                             \
-    else if (Qg) for (int p = __ldg(S.P_cptr + j); p < __ldg(S.P_cptr + j + 1); p++) {                      \
-      const int k = __ldg(S.P_row + p);                                                                     \
+    else if (Qg) for (int p = __ldg(S.P_cptr + (j)); p < __ldg(S.P_cptr + (j + 1)); p++) {                      \
+      const int k = __ldg(S.P_row + (p));                                                                     \
       px += 0.5 * (Qg[k * n + j] + Qg[j * n + k]) * v[k];                                                   \
     }                                                                                                       \
     return px;                                                                                              \
@@ -406,12 +406,23 @@ struct QPSolver {
     if (approximate) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
     const double cinv = 1.0 / c;
     // unscaled: v[0]=pri_res v[1]=|z/E| v[2]=|Ax/E| v[3]=dua_res*c v[4]=|q/D| v[5]=|A'y/D| v[6]=|Px/D|
-    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    // v[7], lhs: first stage of the primal-infeasibility certificate (|E dy|_inf, u'dy+ + l'dy-), v[8], qd: of the
+    // dual one (|D dx|_inf, q'dx) -- the quantities primal_infeasible / dual_infeasible start with, gathered in the
+    // same pass and the same reduction, so that those functions (loops + reductions of their own) only run when
+    // their first stage holds.  Same values, same order of accumulation, same decisions as calling them outright.
+    double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     double u[7] = {0, 0, 0, 0, 0, 0, 0};
+    double sums[2] = {0.0, 0.0};  // lhs, qd
+    const bool cert = !sc;        // the rho update (sc) keeps the plain flow
     for (int r = tid; r < m_lin; r += TEAM) {
       const double ax = lin_row_dot(r, W_x), ei = 1.0 / W_El[r], z = W_zl[r];
       v[0] = fmax(v[0], fabs((ax - z) * ei)); v[1] = fmax(v[1], fabs(z * ei)); v[2] = fmax(v[2], fabs(ax * ei));
       u[0] = fmax(u[0], fabs(ax - z)); u[1] = fmax(u[1], fabs(z)); u[2] = fmax(u[2], fabs(ax));
+      if (cert) {
+        const double dy = proj_dy(W_dyl[r], W_ll[r], W_ul[r]);
+        v[7] = fmax(v[7], fabs(W_El[r] * dy));
+        sums[0] += W_ul[r] * fmax(dy, 0.0) + W_ll[r] * fmin(dy, 0.0);
+      }
     }
     for (int i = tid; i < m_nl; i += TEAM) {
       const int eq = __ldg(S.row_eq + (i));
@@ -420,6 +431,11 @@ struct QPSolver {
       double ei = 1.0 / W_Ep[i], z = W_zp[i];
       v[0] = fmax(v[0], fabs((ax - z) * ei)); v[1] = fmax(v[1], fabs(z * ei)); v[2] = fmax(v[2], fabs(ax * ei));
       u[0] = fmax(u[0], fabs(ax - z)); u[1] = fmax(u[1], fabs(z)); u[2] = fmax(u[2], fabs(ax));
+      if (cert) {
+        const double dy = proj_dy(W_dyp[i], W_lp[i], W_up[i]);
+        v[7] = fmax(v[7], fabs(W_Ep[i] * dy));
+        sums[0] += a.kd * (W_up[i] * fmax(dy, 0.0) + W_lp[i] * fmin(dy, 0.0));
+      }
       for (int k2 = 0; k2 <= eq; k2++) {
         const int si = k2 * ms + i;
         const double axs = W_bs[si] * W_s[si];
@@ -432,6 +448,12 @@ struct QPSolver {
         const double aty = a.kd * W_sl[si] * W_yp[i] + W_bs[si] * W_ys[si];
         v[3] = fmax(v[3], fabs((qs + aty) * di)); v[4] = fmax(v[4], fabs(qs * di)); v[5] = fmax(v[5], fabs(aty * di));
         u[3] = fmax(u[3], fabs(qs + aty)); u[4] = fmax(u[4], fabs(qs)); u[5] = fmax(u[5], fabs(aty));
+        if (cert) {
+          const double us = OSQP_INFTY * W_Es[si];
+          const double dys = proj_dy(W_dys[si], 0.0, us);
+          v[7] = fmax(v[7], fabs(W_Es[si] * dys));
+          sums[0] += us * fmax(dys, 0.0);
+        }
       }
     }
     for (int i = tid; i < m_nl; i += TEAM) W_wp[i] = a.kd * W_yp[i];
@@ -449,9 +471,28 @@ struct QPSolver {
       v[5] = fmax(v[5], fabs(aty * di)); v[6] = fmax(v[6], fabs(px * di));
       u[3] = fmax(u[3], fabs(q + px + aty)); u[4] = fmax(u[4], fabs(q)); u[5] = fmax(u[5], fabs(aty));
       u[6] = fmax(u[6], fabs(px));
+      if (cert) {
+        const double dy = proj_dy(W_dyb[j], W_lb[j], W_ub[j]);
+        v[7] = fmax(v[7], fabs(W_Eb[j] * dy));
+        sums[0] += W_ub[j] * fmax(dy, 0.0) + W_lb[j] * fmin(dy, 0.0);
+        v[8] = fmax(v[8], fabs(W_D[j] * W_dxv[j]));
+        sums[1] += W_qh[j] * W_dxv[j];
+      }
     }
-    Team<TEAM>::reduce_max(v, W_red);
-    if (sc) {
+    if (cert)
+      for (int i = tid; i < m_nl; i += TEAM)  // after the variables: the order dual_infeasible accumulates in
+        for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) {
+          const int si = k2 * ms + i;
+          v[8] = fmax(v[8], fabs(W_Ds[si] * W_dss[si]));
+          sums[1] += c * a.pi * W_Ds[si] * W_dss[si];
+        }
+    if (cert) {
+      Team<TEAM>::template reduce_mixed<9, 2>(v, sums, W_red);
+    } else {
+      double v7[7];
+      for (int k = 0; k < 7; k++) v7[k] = v[k];
+      Team<TEAM>::reduce_max(v7, W_red);
+      for (int k = 0; k < 7; k++) v[k] = v7[k];
       Team<TEAM>::reduce_max(u, W_red);
       for (int k = 0; k < 7; k++) sc[k] = u[k];
     }
@@ -464,8 +505,10 @@ struct QPSolver {
     const bool prim_ok = pri_res < eps_p, dual_ok = dua_res < eps_d;
     if (prim_ok && dual_ok) return approximate ? 2 : 1;
     bool pinf = false, dinf = false;
-    if (!prim_ok) pinf = primal_infeasible(epi);
-    if (!dual_ok) dinf = dual_infeasible(edi);
+    // the certificate functions re-derive their first stage; they are only entered when it holds (always, on the
+    // rho-update path, where it was not gathered)
+    if (!prim_ok && (!cert || (v[7] > epi && sums[0] < -epi * v[7]))) pinf = primal_infeasible(epi);
+    if (!dual_ok && (!cert || (v[8] > edi && sums[1] < -(c * edi * v[8])))) dinf = dual_infeasible(edi);
     if (pinf) return approximate ? 3 : -3;
     if (dinf) return approximate ? 4 : -4;
     return 0;
@@ -593,19 +636,6 @@ struct QPSolver {
 #define SCO_PH(k)
 #endif
 
-  // ---- rare path of the fast loop, kept out of line (and out of its register budget): entries beyond the ones a
-  // thread keeps in registers.  which = 0: linear rows of a variable's column, 1: its penalty rows,
-  // 2: a linear row, 3: a penalty row (p2 = offset from the shared-memory to the global entry index)
-  __device__ __noinline__ double fast_overflow(int which, int p0, int p1, int p2, double acc) {
-    const QPW &wq = this->w;
-    const DevStruct &SS = this->S;
-    if (which == 0) for (int p = p0; p < p1; p++) acc = fma(wq.Als[__ldg(SS.lin_centry + p)], wq.wl[__ldg(SS.lin_crow + p)], acc);
-    else if (which == 1) for (int p = p0; p < p1; p++) acc = fma(wq.Js[__ldg(SS.pc_e + p)], wq.wp[__ldg(SS.pc_r + p)], acc);
-    else if (which == 2) for (int p = p0; p < p1; p++) acc = fma(wq.Als[p], wq.xt2[__ldg(SS.lin_col + p)], acc);
-    else for (int p = p0; p < p1; p++) acc = fma(wq.Js[p], wq.xt2[__ldg(SS.jcol_g + p + p2)], acc);
-    return acc;
-  }
-
   // ================================================================== the ADMM loop, ONE THREAD PER ENTITY
   // Same iteration as generic_loop below (same formulas in the same order; y / rho is y * (1 / rho) as in the
   // reference's rho_inv_vec), different machine mapping: a thread owns ONE entity for the whole QP --
@@ -626,8 +656,8 @@ struct QPSolver {
   // function holding the state of all three roles needs ~150 registers; a 512-thread team has 128).  All of them
   // execute the same sequence of team barriers; the barrier only counts arrivals.
   // Requires ceil32(n) + ceil32(m_lin) + ceil32(m_nl) <= TEAM and no adaptive rho.
-#define SCO_EN 6
-#define SCO_EH 3
+#define SCO_EN 8
+#define SCO_EH 4
   // Everything the hot loop needs, by value: a handful of shared-memory offsets and scalars.  The loop must not touch
   // the solver object (QPW offsets, settings, index arrays live in local memory: with 512 threads per team and
   // ~150 KB of shared memory the L1 that backs local memory is a few dozen KB, and every such access is an L2 round
@@ -673,229 +703,243 @@ struct QPSolver {
     sync();
     int status = 0;
     if (can_check) {
+#ifdef SCO_TIMING
+      const long long tc0 = clock64();
+#endif
       status = check(0, res.pri_res, res.dua_res, nullptr);
+#ifdef SCO_TIMING
+      res.cyc_check += clock64() - tc0;
+#endif
       if (status == 0) sync();
     }
     return status;
   }
 
-  template <int ROLE>  // 0 variable, 1 linear row, 2 penalty row, 3 none (idle warps still do their share of S^-1 rhs)
+  template <int ROLE>  // 0 variable, 1 linear row, 2 penalty row of a structure without equality rows, 4 penalty row (one or two
+  // slacks), 3 none (idle warps still do their share of S^-1 rhs)
   __device__ __noinline__ int fast_role(const FastCtx f, int &iter_out, bool &checked_out, QPResult &res) {
+    constexpr bool PEN = ROLE == 2 || ROLE == 4, EQS = ROLE == 4;
     const int id = f.id, n = f.n;
     const bool act = f.act != 0;
-    // ---- entries.  Unused slots multiply the coefficient 0 with ps[0], which always holds a finite number.
-    double ec[SCO_EN];
-    int ea[SCO_EN];
-#pragma unroll
-    for (int k = 0; k < SCO_EN; k++) { ec[k] = 0.0; ea[k] = f.o_ps; }
-    int ovA0 = 0, ovA1 = 0, ovB0 = 0, ovB1 = 0, ovC = 0;  // entries beyond the register slots (rare)
-    // ---- state and constants of the entity
-    double x = 0.0, zb = 0.0, yb = 0.0, qh = 0.0, bx = 0.0, rb = 1.0, rbi = 1.0, lb = 0.0, ub = 0.0;   // variable
-    double z = 0.0, y = 0.0, rr = 1.0, rri = 1.0, lo = 0.0, hi = 0.0;                                   // row (lin / pen)
-    double mi11 = 0.0, mi12 = 0.0, mi22 = 0.0;                                                          // pen
-    double s1 = 0.0, zs1 = 0.0, ys1 = 0.0, sl1 = 0.0, bs1 = 0.0, rs1 = 1.0, rsi1 = 1.0, cd1 = 0.0, us1 = 0.0, hs1 = 0.0, g1 = 0.0;
-    double s2 = 0.0, zs2 = 0.0, ys2 = 0.0, sl2 = 0.0, bs2 = 0.0, rs2 = 1.0, rsi2 = 1.0, cd2 = 0.0, us2 = 0.0, hs2 = 0.0, g2 = 0.0;
-    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, d4 = 0.0;  // deltas of the last iteration (certificates)
-    int eq = 0;
-    {
-      // one-time loads through the solver object (see FastCtx)
-      const QPW &wq = this->w;
-      const DevStruct &SS = this->S;
-      const int m_lin = this->m_lin, m_nl = this->m_nl, ms = f.ms;
-      if (ROLE == 0 && act) {
-        const int j = id;
-        qh = wq.qh[j]; bx = wq.bx[j]; rb = wq.rb[j]; rbi = 1.0 / rb; lb = wq.lb[j]; ub = wq.ub[j];
-        int pl0 = 0, pl1 = 0, pp0 = 0, pp1 = 0;
-        if (m_lin) { pl0 = __ldg(SS.lin_cptr + j); pl1 = __ldg(SS.lin_cptr + j + 1); }
-        if (m_nl) { pp0 = __ldg(SS.pc_ptr + j); pp1 = __ldg(SS.pc_ptr + j + 1); }
-#pragma unroll
-        for (int k = 0; k < SCO_EH; k++) {
-          if (pl0 + k < pl1) {
-            ec[k] = wq.Als[__ldg(SS.lin_centry + pl0 + k)];
-            ea[k] = f.o_wl + __ldg(SS.lin_crow + pl0 + k);
-          }
-          if (pp0 + k < pp1) {
-            ec[SCO_EH + k] = wq.Js[__ldg(SS.pc_e + pp0 + k)];
-            ea[SCO_EH + k] = f.o_wp + __ldg(SS.pc_r + pp0 + k);
-          }
-        }
-        ovA0 = pl0 + SCO_EH; ovA1 = pl1; ovB0 = pp0 + SCO_EH; ovB1 = pp1;
-      } else if (ROLE == 1 && act) {
-        const int r = id;
-        rr = wq.rl[r]; rri = 1.0 / rr; lo = wq.ll[r]; hi = wq.ul[r];
-        const int p0 = __ldg(SS.lin_rowptr + r), p1 = __ldg(SS.lin_rowptr + r + 1);
-#pragma unroll
-        for (int k = 0; k < SCO_EN; k++)
-          if (p0 + k < p1) { ec[k] = wq.Als[p0 + k]; ea[k] = f.o_xt2 + __ldg(SS.lin_col + p0 + k); }
-        ovA0 = p0 + SCO_EN; ovA1 = p1;
-      } else if (ROLE == 2 && act) {
-        const int i = id;
-        eq = __ldg(SS.row_eq + i);
-        rr = wq.rp[i]; rri = 1.0 / rr; lo = wq.lp[i]; hi = wq.up[i];
-        mi11 = wq.Minv[3 * i]; mi12 = wq.Minv[3 * i + 1]; mi22 = wq.Minv[3 * i + 2];
-        sl1 = wq.sl[i]; bs1 = wq.bs[i]; rs1 = wq.rs[i]; rsi1 = 1.0 / rs1; cd1 = f.cpi * wq.Ds[i]; us1 = OSQP_INFTY * wq.Es[i]; hs1 = wq.hs[i];
-        if (eq) {
-          const int i2 = ms + i;
-          sl2 = wq.sl[i2]; bs2 = wq.bs[i2]; rs2 = wq.rs[i2]; rsi2 = 1.0 / rs2; cd2 = f.cpi * wq.Ds[i2]; us2 = OSQP_INFTY * wq.Es[i2]; hs2 = wq.hs[i2];
-        }
-        const int so = __ldg(SS.row_soff + i), go = __ldg(SS.row_goff + i), wd = __ldg(SS.row_w + i);
-#pragma unroll
-        for (int k = 0; k < SCO_EN; k++)
-          if (k < wd) { ec[k] = wq.Js[so + k]; ea[k] = f.o_xt2 + __ldg(SS.jcol_g + go + k); }
-        ovA0 = so + SCO_EN; ovA1 = so + wd; ovC = go - so;  // overflow: Js[p], column jcol_g[p + ovC]
-      }
-    }
-    const bool overflow = ovA0 < ovA1 || ovB0 < ovB1;
     const double sigma = f.sigma, alpha = f.alpha, oma = 1.0 - f.alpha, kd = f.kd;
-    const int K3 = f.K3, j3 = f.j3, s3 = f.s3, c0 = f.c0, c1 = f.c1;
-    const bool p3_active = f.p3_active != 0;
-    const int o_Sm = f.o_Sm, o_xt = f.o_xt, o_xt2 = f.o_xt2, o_ps = f.o_ps, o_wl = f.o_wl, o_wp = f.o_wp;
     const int max_iter = f.max_iter, chk = f.chk;
-    int iter, status = 0, next_check = chk ? chk : max_iter + 1;
+    int iter = 0, status = 0, next_check = chk ? chk : max_iter + 1;
     bool checked = false;
-    for (iter = 1; iter <= max_iter; iter++) {
-      const bool can_check = iter == next_check;
+    while (iter < max_iter) {
+      // ---- (re)load the entity: constants, entries of A and iterates, all from shared memory.  This happens at the
+      // start and after every termination test: the test is a call, and whatever lives across a call is given a home
+      // in LOCAL memory by the compiler and re-read from there in every iteration (L1 does not keep it: 98 % misses
+      // measured) -- so nothing is kept across it.  Unused entry slots multiply the coefficient 0 with ps[0], which
+      // always holds a finite number.
+      double ec[SCO_EN];
+      int ea[SCO_EN];
+#pragma unroll
+      for (int k = 0; k < SCO_EN; k++) { ec[k] = 0.0; ea[k] = f.o_ps; }
+      double x = 0.0, zb = 0.0, yb = 0.0, qh = 0.0, bx = 0.0, rb = 1.0, rbi = 1.0, lb = 0.0, ub = 0.0;   // variable
+      double z = 0.0, y = 0.0, rr = 1.0, rri = 1.0, lo = 0.0, hi = 0.0;                                   // row (lin / pen)
+      double mi11 = 0.0, mi12 = 0.0, mi22 = 0.0;                                                          // pen
+      double s1 = 0.0, zs1 = 0.0, ys1 = 0.0, sl1 = 0.0, bs1 = 0.0, rs1 = 1.0, rsi1 = 1.0, cd1 = 0.0, us1 = 0.0, hs1 = 0.0, g1 = 0.0;
+      double s2 = 0.0, zs2 = 0.0, ys2 = 0.0, sl2 = 0.0, bs2 = 0.0, rs2 = 1.0, rsi2 = 1.0, cd2 = 0.0, us2 = 0.0, hs2 = 0.0, g2 = 0.0;
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, d4 = 0.0;  // deltas of the last iteration (certificates)
+      int eq = 0;
+      {
+        const QPW &wq = this->w;
+        const DevStruct &SS = this->S;
+        const int m_lin = this->m_lin, m_nl = this->m_nl, ms = f.ms;
+        if (ROLE == 0 && act) {
+          const int j = id;
+          x = wq.x[j]; zb = wq.zb[j]; yb = wq.yb[j];
+          qh = wq.qh[j]; bx = wq.bx[j]; rb = wq.rb[j]; rbi = 1.0 / rb; lb = wq.lb[j]; ub = wq.ub[j];
+          int pl0 = 0, pl1 = 0, pp0 = 0, pp1 = 0;
+          if (m_lin) { pl0 = __ldg(SS.lin_cptr + (j)); pl1 = __ldg(SS.lin_cptr + (j + 1)); }
+          if (m_nl) { pp0 = __ldg(SS.pc_ptr + (j)); pp1 = __ldg(SS.pc_ptr + (j + 1)); }
+#pragma unroll
+          for (int k = 0; k < SCO_EH; k++) {
+            if (pl0 + k < pl1) {
+              ec[k] = wq.Als[__ldg(SS.lin_centry + (pl0 + k))];
+              ea[k] = f.o_wl + __ldg(SS.lin_crow + (pl0 + k));
+            }
+            if (pp0 + k < pp1) {
+              ec[SCO_EH + k] = wq.Js[__ldg(SS.pc_e + (pp0 + k))];
+              ea[SCO_EH + k] = f.o_wp + __ldg(SS.pc_r + (pp0 + k));
+            }
+          }
+        } else if (ROLE == 1 && act) {
+          const int r = id;
+          z = wq.zl[r]; y = wq.yl[r];
+          rr = wq.rl[r]; rri = 1.0 / rr; lo = wq.ll[r]; hi = wq.ul[r];
+          const int p0 = __ldg(SS.lin_rowptr + (r)), p1 = __ldg(SS.lin_rowptr + (r + 1));
+#pragma unroll
+          for (int k = 0; k < SCO_EN; k++)
+            if (p0 + k < p1) { ec[k] = wq.Als[p0 + k]; ea[k] = f.o_xt2 + __ldg(SS.lin_col + (p0 + k)); }
+        } else if (PEN && act) {
+          const int i = id;
+          eq = EQS ? __ldg(SS.row_eq + (i)) : 0;
+          z = wq.zp[i]; y = wq.yp[i];
+          rr = wq.rp[i]; rri = 1.0 / rr; lo = wq.lp[i]; hi = wq.up[i];
+          mi11 = wq.Minv[3 * i]; mi12 = wq.Minv[3 * i + 1]; mi22 = wq.Minv[3 * i + 2];
+          s1 = wq.s[i]; zs1 = wq.zs[i]; ys1 = wq.ys[i];
+          sl1 = wq.sl[i]; bs1 = wq.bs[i]; rs1 = wq.rs[i]; rsi1 = 1.0 / rs1; cd1 = f.cpi * wq.Ds[i]; us1 = OSQP_INFTY * wq.Es[i]; hs1 = wq.hs[i];
+          if (EQS && eq) {
+            const int i2 = ms + i;
+            s2 = wq.s[i2]; zs2 = wq.zs[i2]; ys2 = wq.ys[i2];
+            sl2 = wq.sl[i2]; bs2 = wq.bs[i2]; rs2 = wq.rs[i2]; rsi2 = 1.0 / rs2; cd2 = f.cpi * wq.Ds[i2]; us2 = OSQP_INFTY * wq.Es[i2]; hs2 = wq.hs[i2];
+          }
+          const int so = __ldg(SS.row_soff + (i)), go = __ldg(SS.row_goff + (i)), wd = __ldg(SS.row_w + (i));
+#pragma unroll
+          for (int k = 0; k < SCO_EN; k++)
+            if (k < wd) { ec[k] = wq.Js[so + k]; ea[k] = f.o_xt2 + __ldg(SS.jcol_g + (go + k)); }
+        }
+      }
+      const int K3 = f.K3, j3 = f.j3, s3 = f.s3, c0 = f.c0, c1 = f.c1;
+      const bool p3_active = f.p3_active != 0;
+      const int o_Sm = f.o_Sm, o_xt = f.o_xt, o_xt2 = f.o_xt2, o_ps = f.o_ps, o_wl = f.o_wl, o_wp = f.o_wp;
+      const bool has_pen = f.has_pen != 0;
+      const int seg_end = next_check < max_iter ? next_check : max_iter;
+      // ---- iterations up to (and including) the next tested / last one: no call inside
+      while (iter < seg_end) {
+        iter++;
+#ifdef SCO_TIMING
+        long long tph = clock64();
+#endif
+        // ---- P1: row weights w = rho z - y ; slack elimination (registers -> wl / wp)
+        if (ROLE == 1 && act) {
+          sco_smem[o_wl + id] = rr * z - y;
+        } else if (PEN && act) {
+          const double wpen = rr * z - y;
+          const double kr = kd * rr;
+          const double r1 = sigma * s1 - cd1 + kd * sl1 * wpen + bs1 * (rs1 * zs1 - ys1);
+          if (EQS && eq) {
+            const double r2 = sigma * s2 - cd2 + kd * sl2 * wpen + bs2 * (rs2 * zs2 - ys2);
+            g1 = mi11 * r1 + mi12 * r2;
+            g2 = mi12 * r1 + mi22 * r2;
+            sco_smem[o_wp + id] = kd * wpen - kr * (sl1 * g1 + sl2 * g2);
+          } else {
+            g1 = mi11 * r1;
+            sco_smem[o_wp + id] = kd * wpen - kr * sl1 * g1;
+          }
+        }
+        sync();
+        SCO_PH(0)
+        // ---- P2: reduced right-hand side (variables)
+        if (ROLE == 0 && act) {
+          double acc = 0.0, accp = 0.0;
+#pragma unroll
+          for (int k = 0; k < SCO_EH; k++) {
+            acc = fma(ec[k], sco_smem[ea[k]], acc);
+            accp = fma(ec[SCO_EH + k], sco_smem[ea[SCO_EH + k]], accp);
+          }
+          if (has_pen) acc += accp;
+          sco_smem[o_xt + id] = sigma * x - qh + bx * (rb * zb - yb) + acc;
+        }
+        sync();
+        SCO_PH(1)
+        // ---- P3: partial sums of x~ = S^-1 rhs (every thread of the team, whatever its role)
+        if (p3_active) {
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          int cc = c0;
+          const double *Sc = sco_smem + o_Sm + j3;
+          const double2 *xv = sco_smem2 + (o_xt >> 1);
+#pragma unroll 2
+          for (; cc + 3 < c1; cc += 4) {
+            const double q0 = Sc[cc * n], q1 = Sc[(cc + 1) * n], q2 = Sc[(cc + 2) * n], q3 = Sc[(cc + 3) * n];
+            const double2 x01 = xv[cc >> 1], x23 = xv[(cc >> 1) + 1];  // c0 is a multiple of 4
+            a0 = fma(q0, x01.x, a0);
+            a1 = fma(q1, x01.y, a1);
+            a2 = fma(q2, x23.x, a2);
+            a3 = fma(q3, x23.y, a3);
+          }
+          for (; cc < c1; cc++) a0 = fma(Sc[cc * n], sco_smem[o_xt + cc], a0);
+          sco_smem[o_ps + s3 * n + j3] = (a0 + a2) + (a1 + a3);
+        }
+        sync();
+        SCO_PH(2)
+        // ---- P4a: x~, x and the box rows (variables)
+        if (ROLE == 0 && act) {
+          double xtil = sco_smem[o_ps + id];
+          for (int k = 1; k < K3; k++) xtil += sco_smem[o_ps + k * n + id];
+          sco_smem[o_xt2 + id] = xtil;
+          const double xo = x;
+          const double xn = alpha * xtil + oma * xo;
+          x = xn;
+          const double zt = bx * xtil;
+          const double vv = alpha * zt + oma * zb;
+          const double zn = clampd(vv + yb * rbi, lb, ub);
+          const double dy = rb * (vv - zn);
+          yb += dy;
+          zb = zn;
+          d0 = xn - xo; d1 = dy;
+        }
+        sync();
+        // ---- P4b: rows
+        if ((ROLE == 1 || PEN) && act) {
+          double t = 0.0;
+#pragma unroll
+          for (int k = 0; k < SCO_EN; k++) t = fma(ec[k], sco_smem[ea[k]], t);
+          double zt = t;
+          if (PEN) {
+            {
+              const double stil = g1 - hs1 * t;
+              zt += sl1 * stil;
+              const double so_ = s1;
+              const double sn = alpha * stil + oma * so_;
+              s1 = sn;
+              const double zts = bs1 * stil;
+              const double vs = alpha * zts + oma * zs1;
+              const double zns = clampd(vs + ys1 * rsi1, 0.0, us1);
+              const double dys = rs1 * (vs - zns);
+              ys1 += dys;
+              zs1 = zns;
+              d1 = sn - so_; d2 = dys;
+            }
+            if (EQS && eq) {
+              const double stil = g2 - hs2 * t;
+              zt += sl2 * stil;
+              const double so_ = s2;
+              const double sn = alpha * stil + oma * so_;
+              s2 = sn;
+              const double zts = bs2 * stil;
+              const double vs = alpha * zts + oma * zs2;
+              const double zns = clampd(vs + ys2 * rsi2, 0.0, us2);
+              const double dys = rs2 * (vs - zns);
+              ys2 += dys;
+              zs2 = zns;
+              d3 = sn - so_; d4 = dys;
+            }
+          }
+          const double vv = alpha * zt + oma * z;
+          const double zn = clampd(vv + y * rri, lo, hi);
+          const double dy = rr * (vv - zn);
+          y += dy;
+          z = zn;
+          d0 = dy;
+        }
+        SCO_PH(3)
+      }
+      // ---- iter == seg_end: the tested or the last iteration.  Iterates (+ deltas) -> shared memory, then the test.
+      const int can_check = iter == next_check;
       if (can_check) next_check += chk;
 #ifdef SCO_TIMING
       long long tph = clock64();
 #endif
-      // ---- P1: row weights w = rho z - y ; slack elimination (registers -> wl / wp)
-      if (ROLE == 1 && act) {
-        sco_smem[o_wl + id] = rr * z - y;
-      } else if (ROLE == 2 && act) {
-        const double wpen = rr * z - y;
-        const double kr = kd * rr;
-        const double r1 = sigma * s1 - cd1 + kd * sl1 * wpen + bs1 * (rs1 * zs1 - ys1);
-        if (eq) {
-          const double r2 = sigma * s2 - cd2 + kd * sl2 * wpen + bs2 * (rs2 * zs2 - ys2);
-          g1 = mi11 * r1 + mi12 * r2;
-          g2 = mi12 * r1 + mi22 * r2;
-          sco_smem[o_wp + id] = kd * wpen - kr * (sl1 * g1 + sl2 * g2);
-        } else {
-          g1 = mi11 * r1;
-          sco_smem[o_wp + id] = kd * wpen - kr * sl1 * g1;
-        }
-      }
-      sync();
-      SCO_PH(0)
-      // ---- P2: reduced right-hand side (variables)
-      if (ROLE == 0 && act) {
-        double acc = 0.0, accp = 0.0;
-#pragma unroll
-        for (int k = 0; k < SCO_EH; k++) {
-          acc = fma(ec[k], sco_smem[ea[k]], acc);
-          accp = fma(ec[SCO_EH + k], sco_smem[ea[SCO_EH + k]], accp);
-        }
-        if (overflow) {
-          acc = fast_overflow(0, ovA0, ovA1, 0, acc);
-          accp = fast_overflow(1, ovB0, ovB1, 0, accp);
-        }
-        if (f.has_pen) acc += accp;
-        sco_smem[o_xt + id] = sigma * x - qh + bx * (rb * zb - yb) + acc;
-      }
-      sync();
-      SCO_PH(1)
-      // ---- P3: partial sums of x~ = S^-1 rhs (every thread of the team, whatever its role)
-      if (p3_active) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int cc = c0;
-        const double *Sc = sco_smem + o_Sm + j3;
-        const double2 *xv = sco_smem2 + (o_xt >> 1);
-#pragma unroll 2
-        for (; cc + 3 < c1; cc += 4) {
-          const double q0 = Sc[cc * n], q1 = Sc[(cc + 1) * n], q2 = Sc[(cc + 2) * n], q3 = Sc[(cc + 3) * n];
-          const double2 x01 = xv[cc >> 1], x23 = xv[(cc >> 1) + 1];  // c0 is a multiple of 4
-          a0 = fma(q0, x01.x, a0);
-          a1 = fma(q1, x01.y, a1);
-          a2 = fma(q2, x23.x, a2);
-          a3 = fma(q3, x23.y, a3);
-        }
-        for (; cc < c1; cc++) a0 = fma(Sc[cc * n], sco_smem[o_xt + cc], a0);
-        sco_smem[o_ps + s3 * n + j3] = (a0 + a2) + (a1 + a3);
-      }
-      sync();
-      SCO_PH(2)
-      // ---- P4a: x~, x and the box rows (variables)
-      if (ROLE == 0 && act) {
-        double xtil = sco_smem[o_ps + id];
-        for (int k = 1; k < K3; k++) xtil += sco_smem[o_ps + k * n + id];
-        sco_smem[o_xt2 + id] = xtil;
-        const double xo = x;
-        const double xn = alpha * xtil + oma * xo;
-        x = xn;
-        const double zt = bx * xtil;
-        const double vv = alpha * zt + oma * zb;
-        const double zn = clampd(vv + yb * rbi, lb, ub);
-        const double dy = rb * (vv - zn);
-        yb += dy;
-        zb = zn;
-        d0 = xn - xo; d1 = dy;
-      }
-      sync();
-      // ---- P4b: rows
-      if ((ROLE == 1 || ROLE == 2) && act) {
-        double t = 0.0;
-#pragma unroll
-        for (int k = 0; k < SCO_EN; k++) t = fma(ec[k], sco_smem[ea[k]], t);
-        if (overflow) t = fast_overflow(ROLE == 1 ? 2 : 3, ovA0, ovA1, ovC, t);
-        double zt = t;
-        if (ROLE == 2) {
-          {
-            const double stil = g1 - hs1 * t;
-            zt += sl1 * stil;
-            const double so_ = s1;
-            const double sn = alpha * stil + oma * so_;
-            s1 = sn;
-            const double zts = bs1 * stil;
-            const double vs = alpha * zts + oma * zs1;
-            const double zns = clampd(vs + ys1 * rsi1, 0.0, us1);
-            const double dys = rs1 * (vs - zns);
-            ys1 += dys;
-            zs1 = zns;
-            d1 = sn - so_; d2 = dys;
-          }
-          if (eq) {
-            const double stil = g2 - hs2 * t;
-            zt += sl2 * stil;
-            const double so_ = s2;
-            const double sn = alpha * stil + oma * so_;
-            s2 = sn;
-            const double zts = bs2 * stil;
-            const double vs = alpha * zts + oma * zs2;
-            const double zns = clampd(vs + ys2 * rsi2, 0.0, us2);
-            const double dys = rs2 * (vs - zns);
-            ys2 += dys;
-            zs2 = zns;
-            d3 = sn - so_; d4 = dys;
-          }
-        }
-        const double vv = alpha * zt + oma * z;
-        const double zn = clampd(vv + y * rri, lo, hi);
-        const double dy = rr * (vv - zn);
-        y += dy;
-        z = zn;
-        d0 = dy;
-      }
-      SCO_PH(3)
-      checked = false;
-      if (can_check || iter == max_iter) {
-        if (ROLE == 0) status = fast_flush<0>(id, act, 0, can_check, res, x, zb, yb, 0, 0, 0, 0, 0, d0, d1, 0, 0, 0);
-        else if (ROLE == 1) status = fast_flush<1>(id, act, 0, can_check, res, z, y, 0, 0, 0, 0, 0, 0, d0, 0, 0, 0, 0);
-        else if (ROLE == 2) status = fast_flush<2>(id, act, eq, can_check, res, z, y, s1, zs1, ys1, s2, zs2, ys2, d0, d1, d2, d3, d4);
-        else status = fast_flush<3>(id, 0, 0, can_check, res, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-        checked = can_check;
-        if (status != 0) break;
-      }
+      if (ROLE == 0) status = fast_flush<0>(id, act, 0, can_check, res, x, zb, yb, 0, 0, 0, 0, 0, d0, d1, 0, 0, 0);
+      else if (ROLE == 1) status = fast_flush<1>(id, act, 0, can_check, res, z, y, 0, 0, 0, 0, 0, 0, d0, 0, 0, 0, 0);
+      else if (PEN) status = fast_flush<2>(id, act, eq, can_check, res, z, y, s1, zs1, ys1, s2, zs2, ys2, d0, d1, d2, d3, d4);
+      else status = fast_flush<3>(id, 0, 0, can_check, res, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+      checked = can_check != 0;
       SCO_PH(4)
+      if (status != 0) break;
     }
-    iter_out = iter;
+    iter_out = status != 0 ? iter : max_iter + 1;  // generic_loop's convention: the loop variable after the loop
     checked_out = checked;
     return status;
   }
 
   // roles start on warp boundaries: ceil32(n) variable lanes, ceil32(m_lin) linear-row lanes, ceil32(m_nl) penalty-row lanes
+  // ... and every row of A has at most SCO_EN entries, every column at most SCO_EH from linear and SCO_EH from
+  // penalty rows (S.fast_ok, checked once by sco_create)
   __device__ __forceinline__ bool fast_fits() const {
-    return ((n + 31) & ~31) + ((m_lin + 31) & ~31) + ((m_nl + 31) & ~31) <= TEAM;
+    return S.fast_ok && ((n + 31) & ~31) + ((m_lin + 31) & ~31) + ((m_nl + 31) & ~31) <= TEAM;
   }
 
   __device__ __noinline__ int fast_loop(int &iter_out, bool &checked_out, QPResult &res) {
@@ -919,10 +963,19 @@ struct QPSolver {
     f.max_iter = this->st.max_iter; f.chk = this->st.check_termination; f.has_pen = m_nl != 0;
     f.sigma = this->st.sigma; f.alpha = this->st.alpha; f.kd = this->a.kd; f.cpi = this->c * this->a.pi;
     for (int e = tid; e < f.K3 * n; e += TEAM) wq.ps[e] = 0.0;  // segments beyond n contribute exact zeros
+    // ADMM starts from x = z = y = 0 (osqp_utils.py:195 builds a new OSQP object per call); fast_role reads its
+    // iterates from these arrays
+    for (int j = tid; j < n; j += TEAM) { wq.x[j] = 0.0; wq.zb[j] = 0.0; wq.yb[j] = 0.0; }
+    for (int r = tid; r < m_lin; r += TEAM) { wq.zl[r] = 0.0; wq.yl[r] = 0.0; }
+    for (int i = tid; i < m_nl; i += TEAM) {
+      wq.zp[i] = 0.0; wq.yp[i] = 0.0;
+      wq.s[i] = 0.0; wq.zs[i] = 0.0; wq.ys[i] = 0.0;
+      if (__ldg(this->S.row_eq + (i))) { wq.s[f.ms + i] = 0.0; wq.zs[f.ms + i] = 0.0; wq.ys[f.ms + i] = 0.0; }
+    }
     sync();
     if (role == 0) return fast_role<0>(f, iter_out, checked_out, res);
     if (role == 1) return fast_role<1>(f, iter_out, checked_out, res);
-    if (role == 2) return fast_role<2>(f, iter_out, checked_out, res);
+    if (role == 2) return this->S.nsl == 2 ? fast_role<4>(f, iter_out, checked_out, res) : fast_role<2>(f, iter_out, checked_out, res);
     return fast_role<3>(f, iter_out, checked_out, res);
   }
 
