@@ -572,13 +572,211 @@ def run_b200_arm(args):
     return 0
 
 
+
+# ------------------------------------------------------------------------------ C5: mixed shapes
+def run_mixed(args):
+    """BASELINE.json configs[4]: `--batch` mixed-shape problems per GPU (global problem numbers [rank*B, (rank+1)*B),
+    i.i.d. mixture of nine structures, workloads.gen_mixed), bucketed by structure; every bucket is one launch of its
+    own engine, all buckets of a step run concurrently on their own streams.  Reports verdict counts per bucket, an
+    audit of a random subsample of every bucket against the CPU oracle (rank 0, time-bounded) and the usual line."""
+    import torch
+    import torch.distributed as dist
+    from sco_py_b200 import workloads as W
+    from sco_py_b200.engine import Engine, make_settings
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    t0 = time.time()
+    cores = os.cpu_count() or 1
+    buckets = W.gen_mixed(B, first=rank * B, workers=max(1, min(32, cores // max(world, 1))))
+    t_gen = time.time() - t0
+    settings = make_settings(solver=W.SOLVER_SETTINGS)
+    for bk in buckets:
+        bk["eng"] = Engine(bk["structure"], device=local)
+        bk["d_params"] = torch.as_tensor(bk["params"]).to(dev)
+        bk["d_x0"] = torch.as_tensor(bk["x0"]).to(dev)
+        bk["stream"] = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    cur = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        outs = []
+        for bk in buckets:  # the long buckets first: they decide when the step ends
+            bk["stream"].wait_stream(cur)
+            outs.append(bk["eng"].solve_batch(bk["d_params"], bk["d_x0"], settings, stream=bk["stream"]))
+        for bk in buckets:
+            cur.wait_stream(bk["stream"])
+        return outs
+
+    buckets.sort(key=lambda bk: -bk["structure"].n * len(bk["indices"]))
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    bucket_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in buckets]
+    e0.record(cur)
+    outs = None
+    for k in range(args.steps):
+        if k == args.steps - 1:  # per-bucket device time of the last step
+            outs = []
+            for bk, (a, b) in zip(buckets, bucket_ev):
+                bk["stream"].wait_stream(cur)
+                a.record(bk["stream"])
+                outs.append(bk["eng"].solve_batch(bk["d_params"], bk["d_x0"], settings, stream=bk["stream"]))
+                b.record(bk["stream"])
+            for bk in buckets:
+                cur.wait_stream(bk["stream"])
+        else:
+            step()
+    e1.record(cur)
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler is not None else None
+    rows = []
+    conv_local = 0
+    for bk, out, (a, b) in zip(buckets, outs, bucket_ev):
+        v = out["verdict"].cpu().numpy()
+        stt = out["stats"].cpu().numpy()
+        bk["host"] = {k: t.cpu().numpy() for k, t in out.items()}
+        conv_local += int((v == 1).sum())
+        rows.append([bk["bucket"], len(v), int((v == 1).sum()), int((v == 0).sum()), int((v == -1).sum()),
+                     float(stt[:, 2].astype(np.float64).sum()), float(stt[:, 2].max()), a.elapsed_time(b),
+                     bk["eng"].team, bk["eng"].occupancy])
+    t = torch.tensor([ms_local, float(conv_local)], dtype=torch.float64, device=dev)
+    table = torch.zeros((len(W.MIXED_BUCKETS), 10), dtype=torch.float64, device=dev)
+    for r in rows:
+        table[int(r[0])] = torch.tensor(r, dtype=torch.float64, device=dev)
+    if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        allb = [torch.zeros_like(table) for _ in range(world)]
+        dist.all_gather(allb, table)
+    else:
+        allt, allb = [t], [table]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    per_rank = [a.cpu().tolist() for a in allt]
+    ms_total = max(v[0] for v in per_rank)
+    converged = sum(v[1] for v in per_rank)
+    tabs = np.stack([a.cpu().numpy() for a in allb])  # [world, buckets, 10]
+    bucket_report = []
+    for bi, (name, kw) in enumerate(W.MIXED_BUCKETS):
+        tt = tabs[:, bi, :]
+        n_prob = int(tt[:, 1].sum())
+        if n_prob == 0:
+            continue
+        bucket_report.append({"bucket": bi, "shape": name, "kw": kw, "problems": n_prob, "converged": int(tt[:, 2].sum()),
+                              "failed": int(tt[:, 3].sum()), "iter_cap": int(tt[:, 4].sum()),
+                              "mean_admm_iters": float(tt[:, 5].sum() / n_prob), "max_admm_iters": int(tt[:, 6].max()),
+                              "device_ms_last_step_max_over_ranks": float(tt[:, 7].max()), "team": int(tt[:, 8].max()),
+                              "ctas_per_sm": int(tt[:, 9].max())})
+    # ---- audit (rank 0's problems, every bucket, time-bounded) against the oracle port
+    audits = {}
+    if args.audit > 0 and not args.no_cpu_baseline:
+        per_bucket_s = args.audit_seconds / max(1, len(buckets))
+        for bk in buckets:
+            name = bk["name"]
+            take = np.random.default_rng(12345).permutation(len(bk["indices"]))[:args.audit]
+            arm = MixedCpuArm(name, bk["kw"], args.cpu_cores)
+            out = arm.run([int(bk["indices"][i]) for i in take], per_bucket_s)
+            arm.close()
+            pos = {int(bk["indices"][i]): int(i) for i in take}
+            rel, dvio, match = [], [], 0
+            for r in out["results"]:
+                i = pos[r["index"]]
+                match += int(bool(bk["host"]["verdict"][i] == 1) == r["success"])
+                rel.append(float(np.abs(bk["host"]["x"][i] - r["x"]).max() / max(1.0, np.abs(r["x"]).max())))
+                dvio.append(abs(float(bk["host"]["max_vio"][i]) - r["max_vio"]))
+            audits[str(bk["bucket"])] = {"problems": len(out["results"]), "requested": int(len(take)), "verdict_match": match,
+                                         "rel_dx_max": max(rel) if rel else None, "dvio_max": max(dvio) if dvio else None,
+                                         "wall_s": out["wall"]}
+    value = converged * args.steps / (ms_total * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5 mixed TAMP-shaped subproblems (BASELINE.json configs[4]): 50 % QCQP n/m in "
+                               "(10,15),(20,30),(30,45), 30 % point robot T in 20,40 x K in 1,3, 20 % arm T in 10,20; "
+                               "problem i from default_rng(5000+i)",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": "problems sharded, dp%d" % world,
+                   "pipelining": "the buckets of a step run concurrently on one stream each",
+                   "solver": workload_config(args, "qcqp", B)["solver"]},
+        "clocks": clocks, "gpu_launches": args.steps * len(buckets),
+        "detail": {"converged": int(converged), "problems": B * world, "buckets": bucket_report,
+                   "audit_rank0": audits, "gen_seconds_rank0": t_gen,
+                   "per_rank": [{"rank": r, "ms_per_step": v[0] / args.steps, "converged": int(v[1])} for r, v in enumerate(per_rank)]},
+    }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line))
+    sys.stdout.flush()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _cpu_solve_mixed(job):
+    name, kw, index = job
+    import sqp_port
+    from sco_py_b200 import workloads as W
+    st, params, x0 = W.GENERATORS[name](1, seed_base=W.MIXED_SEED, indices=[index], **kw)
+    r = sqp_port.solve(st, params[0], x0[0], solver=W.SOLVER_SETTINGS)
+    return dict(index=index, success=bool(r["success"]), x=r["x"], max_vio=float(r["max_vio"]),
+                objective=float(r["objective"]), admm_iters=int(r["stats"]["admm_iters"]))
+
+
+class MixedCpuArm(CpuArm):
+    def __init__(self, name, kw, cores=None):
+        CpuArm.__init__(self, name, cores)
+        self.kw = kw
+
+    def run(self, indices, budget_s, on_result=None):
+        import multiprocessing as mp
+        jobs = [(self.name, self.kw, int(i)) for i in indices]
+        t0 = time.time()
+        it = self.pool.imap_unordered(_cpu_solve_mixed, jobs, chunksize=1)
+        results, complete = [], False
+        while True:
+            left = budget_s - (time.time() - t0)
+            if left <= 0:
+                break
+            try:
+                results.append(it.next(timeout=left))
+            except mp.TimeoutError:
+                break
+            except StopIteration:
+                complete = True
+                break
+        return dict(results=results, wall=time.time() - t0, dealt=len(jobs), complete=complete)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="qcqp", choices=["qcqp", "point_robot", "arm"])
+    ap.add_argument("--config", default="qcqp", choices=["qcqp", "point_robot", "arm", "mixed"])
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
     ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (0 = as many as --steps)")
     ap.add_argument("--order", default="index", choices=["index", "profile"],
@@ -598,7 +796,11 @@ def main():
     if world > 1:
         args.gpus = world
     if args.impl == "reference":
+        if args.config == "mixed":
+            args.config = "qcqp"
         return run_reference_arm(args)
+    if args.config == "mixed":
+        return run_mixed(args)
     return run_b200_arm(args)
 
 

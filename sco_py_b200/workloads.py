@@ -61,14 +61,20 @@ def qcqp_structure(n=20, m=30):
     return Structure(n=n, stride=off, Q=Q, q=q, c=Field(-1, False), blocks=[blk])
 
 
-def gen_qcqp(B, n=20, m=30, seed_base=4000, first=0):
+def _indices(B, first, indices):
+    return np.arange(first, first + B) if indices is None else np.asarray(indices, dtype=np.int64)
+
+
+def gen_qcqp(B, n=20, m=30, seed_base=4000, first=0, indices=None):
+    indices = _indices(B, first, indices)
+    B = len(indices)
     st = qcqp_structure(n, m)
     ntri = n * (n + 1) // 2
     params = np.empty((B, st.stride))
     x0 = np.empty((B, n))
     iu = np.triu_indices(n)
     for b in range(B):
-        rng = np.random.default_rng(seed_base + first + b)
+        rng = np.random.default_rng(seed_base + int(indices[b]))
         M = rng.standard_normal((n, n))
         Qm = M.T @ M / n + 0.1 * np.eye(n)
         qv = rng.standard_normal(n)
@@ -106,13 +112,15 @@ def point_robot_structure(T=40, K=3):
                      blocks=[blk], shared=shared)
 
 
-def gen_point_robot(B, T=40, K=3, seed_base=2000, first=0):
+def gen_point_robot(B, T=40, K=3, seed_base=2000, first=0, indices=None):
+    indices = _indices(B, first, indices)
+    B = len(indices)
     st = point_robot_structure(T, K)
     n = st.n
     params = np.zeros((B, st.stride))
     x0 = np.empty((B, n))
     for b in range(B):
-        rng = np.random.default_rng(seed_base + first + b)
+        rng = np.random.default_rng(seed_base + int(indices[b]))
         goal = np.array([10.0, 0.0]) + rng.normal(0.0, 0.5, 2)
         cx = rng.uniform(2.0, 8.0, K)
         cy = rng.normal(0.0, 0.3, K)
@@ -152,15 +160,17 @@ def arm_structure(T=20):
                      blocks=[blk], shared=Qs)
 
 
-def gen_arm(B, T=20, seed_base=3000, first=0, fk=None):
+def gen_arm(B, T=20, seed_base=3000, first=0, fk=None, indices=None):
     if fk is None:
         from .families_host import fk7_pos as fk
+    indices = _indices(B, first, indices)
+    B = len(indices)
     st = arm_structure(T)
     n = st.n
     params = np.zeros((B, st.stride))
     x0 = np.empty((B, n))
     for b in range(B):
-        rng = np.random.default_rng(seed_base + first + b)
+        rng = np.random.default_rng(seed_base + int(indices[b]))
         q0 = rng.uniform(-0.5, 0.5, 7)
         x0[b] = np.tile(q0, T)
         target = fk(q0 + rng.uniform(-0.6, 0.6, 7))
@@ -180,6 +190,75 @@ def _gen_chunk(args):
     name, first, count, kw = args
     _, params, x0 = GENERATORS[name](count, first=first, **kw)
     return first, params, x0
+
+
+# ------------------------------------------------------------------ C5: mixed shapes (BASELINE.json configs[4])
+# i.i.d. mixture, problem i drawn from default_rng(5000 + i): 50 % C4-shaped (n, m) in
+# {(10,15), (20,30), (30,45)}, 30 % C2-shaped T in {20,40} x K in {1,3}, 20 % C3-shaped T in {10,20}.
+MIXED_SEED = 5000
+MIXED_BUCKETS = ([("qcqp", dict(n=n, m=m)) for n, m in ((10, 15), (20, 30), (30, 45))] +
+                 [("point_robot", dict(T=T, K=K)) for T in (20, 40) for K in (1, 3)] +
+                 [("arm", dict(T=T)) for T in (10, 20)])
+
+
+def mixed_bucket_of(i):
+    """Bucket (index into MIXED_BUCKETS) of problem i of the mixed workload."""
+    rng = np.random.default_rng(MIXED_SEED + int(i))
+    u = rng.uniform()
+    if u < 0.5:
+        return int(rng.integers(3))
+    if u < 0.8:
+        return 3 + 2 * int(rng.integers(2)) + int(rng.integers(2))
+    return 7 + int(rng.integers(2))
+
+
+def _bucket_chunk(args):
+    lo, hi = args
+    return lo, np.fromiter((mixed_bucket_of(i) for i in range(lo, hi)), dtype=np.int8, count=hi - lo)
+
+
+def _gen_indexed_chunk(args):
+    name, kw, indices, pos = args
+    _, params, x0 = GENERATORS[name](len(indices), seed_base=MIXED_SEED, indices=indices, **kw)
+    return pos, params, x0
+
+
+def gen_mixed(B, first=0, workers=None, pinned=False):
+    """Problems [first, first + B) of the mixed workload, bucketed by structure.
+    -> list of dict(bucket, name, kw, structure, indices (global problem numbers), params, x0), non-empty buckets only.
+    The bucket of every problem and the problems of every bucket are computed by a process pool in index chunks --
+    nothing is stacked row by row in Python."""
+    import multiprocessing as mp
+    import os
+    workers = workers or min(os.cpu_count() or 1, 32)
+    pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
+    mapper = pool.imap_unordered if pool else map
+    step = max(1024, (B + 8 * workers - 1) // (8 * workers))
+    bucket = np.empty(B, dtype=np.int8)
+    for lo, arr in mapper(_bucket_chunk, [(first + s, min(first + s + step, first + B)) for s in range(0, B, step)]):
+        bucket[lo - first:lo - first + len(arr)] = arr
+    out = []
+    for bi, (name, kw) in enumerate(MIXED_BUCKETS):
+        idx = first + np.nonzero(bucket == bi)[0]
+        if idx.size == 0:
+            continue
+        st = GENERATORS[name](1, **kw)[0]
+        if pinned:
+            import torch
+            params = torch.empty((idx.size, st.stride), dtype=torch.float64, pin_memory=True).numpy()
+            x0 = torch.empty((idx.size, st.n), dtype=torch.float64, pin_memory=True).numpy()
+        else:
+            params, x0 = np.empty((idx.size, st.stride)), np.empty((idx.size, st.n))
+        chunk = max(64, (idx.size + 4 * workers - 1) // (4 * workers))
+        jobs = [(name, kw, idx[s:s + chunk], s) for s in range(0, idx.size, chunk)]
+        for pos, p, x in mapper(_gen_indexed_chunk, jobs):
+            params[pos:pos + p.shape[0]] = p
+            x0[pos:pos + p.shape[0]] = x
+        out.append(dict(bucket=bi, name=name, kw=kw, structure=st, indices=idx, params=params, x0=x0))
+    if pool:
+        pool.close()
+        pool.join()
+    return out
 
 
 def gen_batch(name, B, first=0, workers=None, out_params=None, out_x0=None, **kw):

@@ -44,3 +44,27 @@ def test_mixed_batch_matches_the_oracle_per_problem():
         assert (verdict[i] == 1) == ref["success"], (i, st.n, st.m_nl)
         assert np.abs(xs[i] - ref["x"]).max() <= 1e-4 * max(1.0, np.abs(ref["x"]).max()), (i, st.n, st.m_nl)
         assert abs(vio[i] - ref["max_vio"]) <= 1e-5
+
+
+def test_mixed_generator_buckets_every_problem_once():
+    """workloads.gen_mixed (BASELINE.json configs[4]): vectorised bucketing, reproducible per problem."""
+    bks = W.gen_mixed(600, first=1000, workers=2)
+    idx = np.concatenate([b["indices"] for b in bks])
+    assert sorted(idx.tolist()) == list(range(1000, 1600))
+    for b in bks:
+        assert all(W.mixed_bucket_of(i) == b["bucket"] for i in b["indices"][:5])
+        st, p, x = W.GENERATORS[b["name"]](1, seed_base=W.MIXED_SEED, indices=[int(b["indices"][0])], **b["kw"])
+        assert np.array_equal(p[0], b["params"][0]) and np.array_equal(x[0], b["x0"][0])
+    again = W.gen_mixed(600, first=1000, workers=1)
+    assert all(np.array_equal(a["params"], b["params"]) for a, b in zip(bks, again))
+
+
+@pytest.mark.gpu
+def test_bucketed_solve_matches_per_bucket_solves():
+    from sco_py_b200.engine import Engine, make_settings
+    bks = W.gen_mixed(96, workers=2)
+    s = make_settings(solver=W.SOLVER_SETTINGS)
+    outs = buckets.solve_bucketed(bks, s)
+    for b, o in zip(bks, outs):
+        ref = Engine(b["structure"]).solve_batch_host(b["params"], b["x0"], s)
+        assert np.array_equal(ref["verdict"], o["verdict"]) and np.array_equal(ref["x"], o["x"])
