@@ -98,13 +98,13 @@ static void build_layout(DevStruct &S, int team) {
   };
   const int n = S.n, ml = S.m_lin, mp = S.m_nl, sl = S.nsl * S.m_nl;
   L.Js = take(S.sjnnz); L.S = take(n * n); L.Als = take(S.nnz_lin);
-  L.x = take(n); L.xt = take(n); L.xt2 = take(n); L.qh = take(n); L.D = take(n); L.bx = take(n);
+  L.x = take(n); L.xt = take(n); L.xt2 = take(n + 4); L.qh = take(n); L.D = take(n); L.bx = take(n);  // xt2, wp: + 4 = zero padding
   L.rb = take(n); L.lb = take(n); L.ub = take(n); L.zb = take(n); L.yb = take(n); L.Eb = take(n);
   L.dxv = take(n); L.dyb = take(n); L.xs = take(n);
   L.El = take(ml); L.rl = take(ml); L.ll = take(ml); L.ul = take(ml); L.zl = take(ml); L.yl = take(ml);
   L.wl = take(ml); L.dyl = take(ml);
   L.Ep = take(mp); L.rp = take(mp); L.lp = take(mp); L.up = take(mp); L.zp = take(mp); L.yp = take(mp);
-  L.wp = take(mp); L.bb = take(mp); L.fv = take(mp); L.dyp = take(mp);
+  L.wp = take(mp + 4); L.bb = take(mp); L.fv = take(mp); L.dyp = take(mp);
   L.s = take(sl); L.Ds = take(sl); L.sl = take(sl); L.bs = take(sl); L.zs = take(sl); L.ys = take(sl);
   L.Es = take(sl); L.gs = take(sl); L.hs = take(sl); L.rs = take(sl); L.dss = take(sl); L.dys = take(sl);
   L.Minv = take(3 * mp);
@@ -380,6 +380,9 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
     for (int i = 0; i < m_nl; i++) ok = ok && row_w[i] <= 8;
     for (int j = 0; j < n; j++) ok = ok && lcptr[j + 1] - lcptr[j] <= 4 && pc_ptr[j + 1] - pc_ptr[j] <= 4;
     S.fast_ok = ok ? 1 : 0;
+    bool dense = desc->m_lin == 0 && n <= 32 && m_nl > 0 && m_nl <= 48;
+    for (int i = 0; i < m_nl; i++) dense = dense && row_w[i] == n;
+    S.fast_dense = dense && !ok ? 1 : 0;
   }
   if (rc) { sco_destroy(h); return SCO_ERR_CUDA; }
   // ---- dense fast path: one dense hinge block, no linear rows, sizes within the instantiated table

@@ -668,7 +668,7 @@ struct QPSolver {
     int n, ms;
     int K3, j3, s3, c0, c1, p3_active;  // S^-1 rhs: column segment [c0, c1) of row j3
     int o_Sm, o_xt, o_xt2, o_ps, o_wl, o_wp;  // shared-memory offsets (doubles)
-    int max_iter, chk, has_pen;
+    int max_iter, chk, has_pen, m_nl;
     double sigma, alpha, kd, cpi;
   };
 
@@ -715,10 +715,17 @@ struct QPSolver {
     return status;
   }
 
-  template <int ROLE>  // 0 variable, 1 linear row, 2 penalty row of a structure without equality rows, 4 penalty row (one or two
-  // slacks), 3 none (idle warps still do their share of S^-1 rhs)
+  // DENSE = 1: structures whose penalty rows are dense (QUADFORM / VM rows over all n <= 32 variables, m_nl <= 48,
+  // no linear rows -- the QCQP shapes with more than 32 rows, which the two-warp dense kernel does not take): a
+  // penalty-row thread keeps its whole row of J (SCO_DN coefficients), a variable thread its whole column (SCO_DM),
+  // operands are read with broadcast 128-bit loads; no addresses are stored.
+#define SCO_DN 32
+#define SCO_DM 48
+  template <int ROLE, int DENSE>  // ROLE: 0 variable, 1 linear row, 2 penalty row of a structure without equality rows,
+  // 4 penalty row (one or two slacks), 3 none (idle warps still do their share of S^-1 rhs)
   __device__ __noinline__ int fast_role(const FastCtx f, int &iter_out, bool &checked_out, QPResult &res) {
     constexpr bool PEN = ROLE == 2 || ROLE == 4, EQS = ROLE == 4;
+    constexpr int NEC = DENSE ? (ROLE == 0 ? SCO_DM : SCO_DN) : SCO_EN;  // coefficient slots of this role
     const int id = f.id, n = f.n;
     const bool act = f.act != 0;
     const double sigma = f.sigma, alpha = f.alpha, oma = 1.0 - f.alpha, kd = f.kd;
@@ -731,10 +738,12 @@ struct QPSolver {
       // in LOCAL memory by the compiler and re-read from there in every iteration (L1 does not keep it: 98 % misses
       // measured) -- so nothing is kept across it.  Unused entry slots multiply the coefficient 0 with ps[0], which
       // always holds a finite number.
-      double ec[SCO_EN];
+      double ec[NEC];
       int ea[SCO_EN];
 #pragma unroll
-      for (int k = 0; k < SCO_EN; k++) { ec[k] = 0.0; ea[k] = f.o_ps; }
+      for (int k = 0; k < NEC; k++) ec[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < SCO_EN; k++) ea[k] = f.o_ps;
       double x = 0.0, zb = 0.0, yb = 0.0, qh = 0.0, bx = 0.0, rb = 1.0, rbi = 1.0, lb = 0.0, ub = 0.0;   // variable
       double z = 0.0, y = 0.0, rr = 1.0, rri = 1.0, lo = 0.0, hi = 0.0;                                   // row (lin / pen)
       double mi11 = 0.0, mi12 = 0.0, mi22 = 0.0;                                                          // pen
@@ -753,6 +762,11 @@ struct QPSolver {
           int pl0 = 0, pl1 = 0, pp0 = 0, pp1 = 0;
           if (m_lin) { pl0 = __ldg(SS.lin_cptr + (j)); pl1 = __ldg(SS.lin_cptr + (j + 1)); }
           if (m_nl) { pp0 = __ldg(SS.pc_ptr + (j)); pp1 = __ldg(SS.pc_ptr + (j + 1)); }
+          if (DENSE) {  // column j of the dense J: entry (row k, column j)
+#pragma unroll
+            for (int k = 0; k < NEC; k++)
+              if (k < m_nl) ec[k] = wq.Js[__ldg(SS.row_soff + (k)) + j];
+          } else
 #pragma unroll
           for (int k = 0; k < SCO_EH; k++) {
             if (pl0 + k < pl1) {
@@ -786,6 +800,11 @@ struct QPSolver {
             sl2 = wq.sl[i2]; bs2 = wq.bs[i2]; rs2 = wq.rs[i2]; rsi2 = 1.0 / rs2; cd2 = f.cpi * wq.Ds[i2]; us2 = OSQP_INFTY * wq.Es[i2]; hs2 = wq.hs[i2];
           }
           const int so = __ldg(SS.row_soff + (i)), go = __ldg(SS.row_goff + (i)), wd = __ldg(SS.row_w + (i));
+          if (DENSE) {
+#pragma unroll
+            for (int k = 0; k < NEC; k++)
+              if (k < n) ec[k] = wq.Js[so + k];
+          } else
 #pragma unroll
           for (int k = 0; k < SCO_EN; k++)
             if (k < wd) { ec[k] = wq.Js[so + k]; ea[k] = f.o_xt2 + __ldg(SS.jcol_g + (go + k)); }
@@ -824,6 +843,21 @@ struct QPSolver {
         // ---- P2: reduced right-hand side (variables)
         if (ROLE == 0 && act) {
           double acc = 0.0, accp = 0.0;
+          if (DENSE) {  // J' w over all penalty rows: four chains, operands by broadcast 128-bit loads
+            double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+            const double2 *wv = sco_smem2 + (o_wp >> 1);
+#pragma unroll
+            for (int k = 0; k < NEC; k += 4) {
+              if (k < f.m_nl) {  // team-uniform; wp is zero-padded to a multiple of four
+                const double2 w01 = wv[k >> 1], w23 = wv[(k >> 1) + 1];
+                b0 = fma(ec[k], w01.x, b0);
+                b1 = fma(ec[k + 1], w01.y, b1);
+                b2 = fma(ec[k + 2], w23.x, b2);
+                b3 = fma(ec[k + 3], w23.y, b3);
+              }
+            }
+            accp = (b0 + b2) + (b1 + b3);
+          } else
 #pragma unroll
           for (int k = 0; k < SCO_EH; k++) {
             acc = fma(ec[k], sco_smem[ea[k]], acc);
@@ -874,6 +908,21 @@ struct QPSolver {
         // ---- P4b: rows
         if ((ROLE == 1 || PEN) && act) {
           double t = 0.0;
+          if (DENSE && PEN) {  // J x~ over all variables
+            double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+            const double2 *xv2 = sco_smem2 + (o_xt2 >> 1);
+#pragma unroll
+            for (int k = 0; k < NEC; k += 4) {
+              if (k < n) {  // xt2 is zero-padded to a multiple of four
+                const double2 x01 = xv2[k >> 1], x23 = xv2[(k >> 1) + 1];
+                b0 = fma(ec[k], x01.x, b0);
+                b1 = fma(ec[k + 1], x01.y, b1);
+                b2 = fma(ec[k + 2], x23.x, b2);
+                b3 = fma(ec[k + 3], x23.y, b3);
+              }
+            }
+            t = (b0 + b2) + (b1 + b3);
+          } else
 #pragma unroll
           for (int k = 0; k < SCO_EN; k++) t = fma(ec[k], sco_smem[ea[k]], t);
           double zt = t;
@@ -939,7 +988,7 @@ struct QPSolver {
   // ... and every row of A has at most SCO_EN entries, every column at most SCO_EH from linear and SCO_EH from
   // penalty rows (S.fast_ok, checked once by sco_create)
   __device__ __forceinline__ bool fast_fits() const {
-    return S.fast_ok && ((n + 31) & ~31) + ((m_lin + 31) & ~31) + ((m_nl + 31) & ~31) <= TEAM;
+    return (S.fast_ok || (S.fast_dense && m_lin == 0)) && ((n + 31) & ~31) + ((m_lin + 31) & ~31) + ((m_nl + 31) & ~31) <= TEAM;
   }
 
   __device__ __noinline__ int fast_loop(int &iter_out, bool &checked_out, QPResult &res) {
@@ -960,7 +1009,7 @@ struct QPSolver {
     f.c1 = (f.s3 + 1) * CS < n ? (f.s3 + 1) * CS : n;
     f.p3_active = f.s3 < f.K3 && f.c0 < n;
     f.o_Sm = wq.Sm.off; f.o_xt = wq.xt.off; f.o_xt2 = wq.xt2.off; f.o_ps = wq.ps.off; f.o_wl = wq.wl.off; f.o_wp = wq.wp.off;
-    f.max_iter = this->st.max_iter; f.chk = this->st.check_termination; f.has_pen = m_nl != 0;
+    f.max_iter = this->st.max_iter; f.chk = this->st.check_termination; f.has_pen = m_nl != 0; f.m_nl = m_nl;
     f.sigma = this->st.sigma; f.alpha = this->st.alpha; f.kd = this->a.kd; f.cpi = this->c * this->a.pi;
     for (int e = tid; e < f.K3 * n; e += TEAM) wq.ps[e] = 0.0;  // segments beyond n contribute exact zeros
     // ADMM starts from x = z = y = 0 (osqp_utils.py:195 builds a new OSQP object per call); fast_role reads its
@@ -972,11 +1021,21 @@ struct QPSolver {
       wq.s[i] = 0.0; wq.zs[i] = 0.0; wq.ys[i] = 0.0;
       if (__ldg(this->S.row_eq + (i))) { wq.s[f.ms + i] = 0.0; wq.zs[f.ms + i] = 0.0; wq.ys[f.ms + i] = 0.0; }
     }
+    // the dense variants read their operands in groups of four: pad wp / xt2 with zeros (the arrays behind them are
+    // rewritten before they are read)
+    if (tid < 4) { wq.wp[m_nl + tid] = 0.0; wq.xt2[n + tid] = 0.0; }
     sync();
-    if (role == 0) return fast_role<0>(f, iter_out, checked_out, res);
-    if (role == 1) return fast_role<1>(f, iter_out, checked_out, res);
-    if (role == 2) return this->S.nsl == 2 ? fast_role<4>(f, iter_out, checked_out, res) : fast_role<2>(f, iter_out, checked_out, res);
-    return fast_role<3>(f, iter_out, checked_out, res);
+    if constexpr (TEAM <= 256) {  // the dense variants need ~200 registers: teams that have them
+      if (!this->S.fast_ok) {
+        if (role == 0) return fast_role<0, 1>(f, iter_out, checked_out, res);
+        if (role == 2) return this->S.nsl == 2 ? fast_role<4, 1>(f, iter_out, checked_out, res) : fast_role<2, 1>(f, iter_out, checked_out, res);
+        return fast_role<3, 0>(f, iter_out, checked_out, res);
+      }
+    }
+    if (role == 0) return fast_role<0, 0>(f, iter_out, checked_out, res);
+    if (role == 1) return fast_role<1, 0>(f, iter_out, checked_out, res);
+    if (role == 2) return this->S.nsl == 2 ? fast_role<4, 0>(f, iter_out, checked_out, res) : fast_role<2, 0>(f, iter_out, checked_out, res);
+    return fast_role<3, 0>(f, iter_out, checked_out, res);
   }
 
   // ================================================================== the ADMM loop
