@@ -462,6 +462,57 @@ def time_config(args, name, B, steps, warmup, dev, local, rank, world, dist, sam
     return res
 
 
+def measure_warm_start(args, eng, main, host):
+    """`--batch` problems again with sco_settings.warm_start = 2 (every penalty QP after a problem's first starts from
+    the previous QP's x and duals): throughput, iteration counts and agreement with the cold-start results."""
+    import torch
+    from sco_py_b200 import workloads as W
+    from sco_py_b200.engine import make_settings
+    B = main["B"]
+    dev = eng.device
+    st0 = eng.st
+    h_params = torch.empty((B, st0.stride), dtype=torch.float64, pin_memory=True)
+    h_x0 = torch.empty((B, st0.n), dtype=torch.float64, pin_memory=True)
+    W.gen_batch(args.config, B, first=0, out_params=h_params.numpy(), out_x0=h_x0.numpy())
+    d_params, d_x0 = h_params.to(dev), h_x0.to(dev)
+    settings = make_settings(solver=W.SOLVER_SETTINGS, warm_start=2)
+    n_streams = max(1, min(args.streams, 8))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    cur = torch.cuda.current_stream(dev)
+    steps = min(args.steps, 4)
+
+    def run(count):
+        outs = []
+        for s_ in streams:
+            s_.wait_stream(cur)
+        for i in range(count):
+            outs.append(eng.solve_batch(d_params, d_x0, settings, stream=streams[i % n_streams]))
+        for s_ in streams:
+            cur.wait_stream(s_)
+        return outs
+
+    run(1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    outs = run(steps)
+    e1.record(cur)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {k: v.cpu().numpy() for k, v in outs[-1].items()}
+    vc, vw = host["verdict"], out["verdict"]
+    same = vc == vw
+    rel = np.abs(host["x"] - out["x"]).max(axis=1) / np.maximum(1.0, np.abs(host["x"]).max(axis=1))
+    conv = int((vw == 1).sum())
+    return {"mode": "sco_settings.warm_start = 2 (opt-in; cold start is the default and the parity mode)",
+            "value": conv / (ms * 1e-3), "unit": UNIT, "steps": steps, "ms_per_step": ms, "converged": conv,
+            "verdicts_equal_to_cold": int(same.sum()), "problems": int(same.size),
+            "rel_dx_vs_cold": {"p50": float(np.percentile(rel[same], 50)), "p99": float(np.percentile(rel[same], 99))},
+            "max_vio_of_converged_max": float(out["max_vio"][vw == 1].max()) if conv else None,
+            "mean_admm_iters": float(out["stats"][:, 2].mean()), "mean_admm_iters_cold": float(host["stats"][:, 2].mean()),
+            "mean_qp_solves": float(out["stats"][:, 1].mean()), "mean_qp_solves_cold": float(host["stats"][:, 1].mean())}
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -507,6 +558,14 @@ def run_b200_arm(args):
     _lib.check(eng.lib.sco_probe_fp64(local, ctypes.byref(tf)))
     roofline = roofline_of(args.config, st, stats, ms_step, tf.value, B)
     team, smem_bytes, occupancy = eng.team, eng.smem_bytes, eng.occupancy
+    # ---- opt-in warm start (sco_settings.warm_start = 2; the reference never warm-starts): same batch, outside the
+    # timed regions of the headline numbers, judged against the cold-start results above
+    warm_report = None
+    if world == 1 and not args.no_warm_start:
+        try:
+            warm_report = measure_warm_start(args, eng, main, host)
+        except Exception as ex:
+            warm_report = {"error": repr(ex)}
     eng.close()
 
     # ---- oracle audit + CPU baseline: one CPU pass over a random subsample of the batch (outside every timed region)
@@ -554,7 +613,7 @@ def run_b200_arm(args):
                    "verdict_counts": {str(k): int((verdict == k).sum()) for k in (-1, 0, 1)},
                    "mean_sqp_iters": float(stats[:, 0].mean()), "mean_qp_solves": float(stats[:, 1].mean()),
                    "mean_admm_iters": float(stats[:, 2].mean()), "max_admm_iters": int(stats[:, 2].max()),
-                   "audit": audit,
+                   "audit": audit, "warm_start": warm_report,
                    "per_rank": [{"rank": r, "ms_per_step": round(v[0], 1), "max_admm_iters": int(v[1]),
                                  "busy_fraction": round(v[0] / ms_step, 3), "total_admm_iters": int(v[2])}
                                 for r, v in enumerate(per_rank)],
@@ -790,6 +849,7 @@ def main():
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU pass (audit and cpu_baseline)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip detail.other_configs (C2 / C3)")
+    ap.add_argument("--no-warm-start", action="store_true", help="skip detail.warm_start (the opt-in warm-start mode)")
     args = ap.parse_args()
     args.cpu_cores = args.cpu_cores or None
     world = int(os.environ.get("WORLD_SIZE", "1"))

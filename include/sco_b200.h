@@ -44,8 +44,9 @@ extern "C" {
 #define SCO_FAM_CIRCLE2D 2 /* f_{t,k} = R_k - |p_t - c_k| ; ipar = {T, K} ; par = c [K][2], R [K]      */
 #define SCO_FAM_FK7 3      /* flange position of a 7-link DH chain on x[n-7:n], finite-difference Jacobian */
 #define SCO_FAM_VM 4       /* rows given as stack programs (sco_py_b200/sym.py): par = m row offsets, then
-                              (opcode, operand) pairs; ipar = {n, m, instructions}; finite-difference Jacobian,
-                              like a black-box Expr without grad (expr.py:61-69) */
+                              (opcode, operand) pairs; ipar = {n, m, instructions, analytic}; analytic = 0:
+                              finite-difference Jacobian, like a black-box Expr without grad (expr.py:61-69);
+                              analytic = 1: the program differentiated in forward mode, like Expr(f, grad) (:86-88) */
 
 #define SCO_CNT_LEQ 0 /* LEqExpr -> hinge penalty, one slack per row  (expr.py:353-371) */
 #define SCO_CNT_EQ 1  /* EqExpr  -> abs penalty, two slacks per row   (expr.py:314-332) */
@@ -112,8 +113,9 @@ typedef struct {
   /* non-quadratic objective term (prob.py:97-103 _nonquad_obj_exprs): one scalar stack program, convexified to
    * degree 2 every SQP iteration -- finite-difference gradient and Hessian, eigenvalue shift (expr.py:102-156) */
   sco_field obj_prog;
-  int32_t obj_prog_len; /* instructions; 0 = none */
-  int32_t pad_;
+  int32_t obj_prog_len;   /* instructions; 0 = none */
+  int32_t obj_prog_flags; /* bit 0: gradient by forward-mode differentiation of the program (Expr(f, grad),
+                             expr.py:86-88) instead of finite differences; the Hessian stays numerical (expr.py:102-109) */
   /* AffExpr objective terms (prob.py:97-103 files them under _quad_obj_exprs): the sum of their A rows, n doubles
    * (their constants go into c).  The exact merit uses a'x (AffExpr.eval, expr.py:173-174); the QP uses
    * w * a'x with the weight of quirk C-4 (prob.py:220-221,240-249,424-426: every update_obj appends another

@@ -111,35 +111,79 @@ def fk7_f(x):
 # ---------------------------------------------------------------- VM (stack programs, C1 toy problems)
 # Independent restatement of the interpreter of sco_py_b200/sym.py (the product's host code): program =
 # m row offsets, then (opcode, operand) pairs; opcodes END 0, PUSH_X 1, PUSH_C 2, ADD 3, SUB 4, MUL 5,
-# DIV 6, NEG 7, POWI 8, SQRT 9, LOG 10, EXP 11, SIN 12, COS 13.
+# DIV 6, NEG 7, POWI 8, SQRT 9, LOG 10, EXP 11, SIN 12, COS 13, ABS 14, MIN 15, MAX 16, TEE 17, LOAD 18 (temporaries).
 
 
-def vm_f(x, prog, m):
+def _vm_run(xv, prog, m, wrt):
+    """Values and d/dx_wrt (wrt = -1: values only) of the m rows; dual numbers as (value, derivative) tuples."""
     import math
-    xv = np.asarray(x, dtype=float).ravel()
     ins = np.asarray(prog[m:], dtype=float).reshape(-1, 2)
-    out = np.zeros((m, 1))
-    unary = {9: math.sqrt, 10: math.log, 11: math.exp, 12: math.sin, 13: math.cos}
+    val, der = np.zeros(m), np.zeros(m)
     for r in range(m):
-        pc, stack = int(prog[r]), []
+        pc, stack, tmp = int(prog[r]), [], {}
         while int(ins[pc, 0]) != 0:
             op, arg = int(ins[pc, 0]), float(ins[pc, 1])
             pc += 1
             if op == 1:
-                stack.append(float(xv[int(arg)]))
+                stack.append((float(xv[int(arg)]), 1.0 if int(arg) == wrt else 0.0))
             elif op == 2:
-                stack.append(arg)
-            elif op in (3, 4, 5, 6):
-                b, a = stack.pop(), stack.pop()
-                stack.append(a + b if op == 3 else a - b if op == 4 else a * b if op == 5 else a / b)
+                stack.append((arg, 0.0))
+            elif op in (3, 4, 5, 6, 15, 16):
+                (b, db), (a, da) = stack.pop(), stack.pop()
+                if op == 3:
+                    stack.append((a + b, da + db))
+                elif op == 4:
+                    stack.append((a - b, da - db))
+                elif op == 5:
+                    stack.append((a * b, da * b + a * db))
+                elif op == 6:
+                    q = a / b
+                    stack.append((q, (da - q * db) / b))
+                elif op == 15:
+                    stack.append((a, da) if a <= b else (b, db))
+                else:
+                    stack.append((a, da) if a >= b else (b, db))
             elif op == 7:
-                stack.append(-stack.pop())
+                a, da = stack.pop()
+                stack.append((-a, -da))
             elif op == 8:
-                a, v = stack.pop(), 1.0
+                a, da = stack.pop()
+                v, vm1 = 1.0, 1.0
                 for _ in range(int(arg)):
+                    vm1 = v
                     v *= a
-                stack.append(v)
+                stack.append((v, int(arg) * vm1 * da if int(arg) > 0 else 0.0))
+            elif op == 14:
+                a, da = stack.pop()
+                stack.append((abs(a), da if a >= 0.0 else -da))
+            elif op == 17:
+                tmp[int(arg)] = stack[-1]
+            elif op == 18:
+                stack.append(tmp[int(arg)])
             else:
-                stack.append(unary[op](stack.pop()))
-        out[r, 0] = stack.pop()
-    return out
+                a, da = stack.pop()
+                if op == 9:
+                    v = math.sqrt(a)
+                    stack.append((v, da / (2.0 * v) if da != 0.0 else 0.0))
+                elif op == 10:
+                    stack.append((math.log(a), da / a))
+                elif op == 11:
+                    v = math.exp(a)
+                    stack.append((v, v * da))
+                elif op == 12:
+                    stack.append((math.sin(a), math.cos(a) * da))
+                else:
+                    stack.append((math.cos(a), -math.sin(a) * da))
+        val[r], der[r] = stack.pop()
+    return val, der
+
+
+def vm_f(x, prog, m):
+    return _vm_run(np.asarray(x, dtype=float).ravel(), prog, m, -1)[0].reshape(m, 1)
+
+
+def vm_grad(x, prog, m):
+    """Exact Jacobian (m, n) of a program: forward mode, one pass per variable -- what a user-supplied `grad` of an
+    `Expr(f, grad)` returns (expr.py:86-88)."""
+    xv = np.asarray(x, dtype=float).ravel()
+    return np.stack([_vm_run(xv, prog, m, j)[1] for j in range(xv.size)], axis=1)

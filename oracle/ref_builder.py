@@ -53,7 +53,8 @@ def build_prob(ref, st, row, x0):
         prob.add_obj_expr(ex.BoundExpr(ex.AffExpr(pp.qa.reshape(1, n), np.zeros((1, 1))), var))
     if pp.obj_prog is not None:  # black-box objective term, as tests/sco_osqp/test_solver.py:66-68 adds it
         import families as fam
-        prob.add_obj_expr(ex.BoundExpr(ex.Expr(lambda x: fam.vm_f(x, pp.obj_prog, 1)), var))
+        og = (lambda x: fam.vm_grad(x, pp.obj_prog, 1)) if getattr(st, "obj_prog_flags", 0) & 1 else None
+        prob.add_obj_expr(ex.BoundExpr(ex.Expr(lambda x: fam.vm_f(x, pp.obj_prog, 1), og), var))
     if st.m_lin:
         A = pp.A_lin.toarray()
         eq = np.isclose(pp.l_lin, pp.u_lin) & np.isfinite(pp.l_lin)
@@ -74,7 +75,7 @@ def build_prob(ref, st, row, x0):
             r = e
     for b in pp.blocks:
         blk = b.blk
-        grad = None if blk.family in (port.FAM_FK7, port.FAM_VM) else b.grad
+        grad = None if blk.family == port.FAM_FK7 or (blk.family == port.FAM_VM and not blk.ipar[3]) else b.grad
         e = ex.Expr(b.f, grad)
         cnt = (ex.EqExpr if blk.cnt_type == port.CNT_EQ else ex.LEqExpr)(e, b.val)
         gids = None

@@ -88,8 +88,10 @@ class _BlockFn(object):
             m, n_instr = blk.m, blk.ipar[2]
             prog = _field(st, blk.par, row, m + 2 * n_instr)
             self.f = lambda x: fam.vm_f(x, prog, m)
-            # a black box without analytic gradient: expr.py:86-87 -> numdifftools.Jacobian
-            self.grad = lambda x: nd.Jacobian(lambda v: fam.vm_f(v, prog, m).ravel())(x)
+            if blk.ipar[3]:  # Expr(f, grad): the user's analytic gradient (expr.py:86-88)
+                self.grad = lambda x: fam.vm_grad(x, prog, m)
+            else:  # a black box without analytic gradient: expr.py:86-87 -> numdifftools.Jacobian
+                self.grad = lambda x: nd.Jacobian(lambda v: fam.vm_f(v, prog, m).ravel())(x)
         else:
             raise NotImplementedError(blk.family)
 
@@ -205,7 +207,10 @@ class PortProblem(object):
             lam = float(np.min(np.linalg.eigvalsh(H)))
             if lam < 0:
                 H = H - np.eye(self.n) * lam
-            g = nd.Jacobian(flat)(self.x)  # (1, n)
+            if getattr(self.st, "obj_prog_flags", 0) & 1:  # Expr(f, grad): analytic gradient, numerical Hessian
+                g = fam.vm_grad(self.x, self.obj_prog, 1)
+            else:
+                g = nd.Jacobian(flat)(self.x)  # (1, n)
             self.Hq = H
             self.aq = (g - self.x.T @ H)[0]
             self.bq = float(0.5 * self.x[:, 0] @ (H @ self.x[:, 0]) - g[0] @ self.x[:, 0] + flat(self.x)[0])

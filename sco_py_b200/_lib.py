@@ -30,7 +30,7 @@ class CStructure(ctypes.Structure):
                 ("Q", CField), ("q", CField), ("c", CField), ("lin_l", CField), ("lin_u", CField),
                 ("lin_rowptr", c_vp), ("lin_col", c_vp), ("lin_val", c_vp), ("shared", c_vp),
                 ("group_overlap", c_vp), ("blocks", CBlock * MAX_BLOCKS),
-                ("obj_prog", CField), ("obj_prog_len", c_i32), ("pad_", c_i32),
+                ("obj_prog", CField), ("obj_prog_len", c_i32), ("obj_prog_flags", c_i32),
                 ("qa", CField), ("lb0", CField), ("ub0", CField)]
 
 

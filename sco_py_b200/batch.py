@@ -160,7 +160,7 @@ def group_key(cp):
     return (cp.x0.size, cp.qa is not None, cp.lb0 is not None,
             None if cp.lin_A is None else (cp.lin_A.shape, cp.lin_A.tobytes()), tuple(cp.gids),
             tuple((b[0].family, b[0].m, b[1], tuple(b[0].ipar), tuple(b[3])) for b in cp.blocks),
-            None if cp.obj_prog is None else cp.obj_prog.n_instr)
+            None if cp.obj_prog is None else (cp.obj_prog.n_instr, cp.obj_prog.analytic))
 
 
 def compile_batch(probs, compiled=None):
@@ -178,7 +178,7 @@ def compile_batch(probs, compiled=None):
                     list(a[0].ipar) == list(b[0].ipar) for a, b in zip(c.blocks, c0.blocks)) and
                 (c.obj_prog is None) == (c0.obj_prog is None) and (c.qa is None) == (c0.qa is None) and
                 (c.lb0 is None) == (c0.lb0 is None) and
-                (c.obj_prog is None or c.obj_prog.n_instr == c0.obj_prog.n_instr))
+                (c.obj_prog is None or (c.obj_prog.n_instr == c0.obj_prog.n_instr and c.obj_prog.analytic == c0.obj_prog.analytic)))
         if not same:
             raise UnsupportedProblem("problem %d of the batch does not share the structure of problem 0" % i)
     shared_parts, shared_off = [], 0
@@ -235,7 +235,7 @@ def compile_batch(probs, compiled=None):
         else:
             of = own_field(p0.size)
             fills.append((of, lambda c: c.obj_prog.params()))
-        kw.update(obj_prog=of, obj_prog_len=c0.obj_prog.n_instr)
+        kw.update(obj_prog=of, obj_prog_len=c0.obj_prog.n_instr, obj_prog_flags=int(c0.obj_prog.analytic))
     blocks = []
     for bi, (fam, ctype, val, gids) in enumerate(c0.blocks):
         p0 = fam.params()
@@ -280,7 +280,7 @@ def signature(st):
     if st.m_lin:
         lin = (st.lin_rowptr.tobytes(), st.lin_col.tobytes(), st.lin_val.tobytes(), fld(st.lin_l), fld(st.lin_u))
     return (st.n, st.stride, fld(st.Q), fld(st.q), fld(st.c), fld(st.qa), fld(st.lb0), fld(st.ub0), fld(st.obj_prog),
-            st.obj_prog_len, st.m_lin, lin, st.n_groups,
+            st.obj_prog_len, st.obj_prog_flags, st.m_lin, lin, st.n_groups,
             None if st.group_overlap is None else st.group_overlap.tobytes(),
             None if st.shared is None else st.shared.tobytes(),
             tuple((b.family, b.cnt_type, b.m, fld(b.par), fld(b.val), tuple(b.ipar), b.group_mask, b.jw)

@@ -36,7 +36,7 @@ def _fld(f):
 
 def structure_to_json(st):
     d = dict(n=int(st.n), stride=int(st.stride), m_lin=int(st.m_lin), n_groups=int(st.n_groups),
-             obj_prog_len=int(st.obj_prog_len))
+             obj_prog_len=int(st.obj_prog_len), obj_prog_flags=int(st.obj_prog_flags))
     for name in _FIELDS:
         d[name] = _fld(getattr(st, name))
     d["blocks"] = [dict(family=int(b.family), cnt_type=int(b.cnt_type), m=int(b.m), par=_fld(b.par), val=_fld(b.val),
@@ -52,7 +52,7 @@ def structure_from_json(d, arrays):
         if name in arrays:
             kw[name] = arrays[name]
     return Structure(n=d["n"], stride=d["stride"], m_lin=d["m_lin"], n_groups=d["n_groups"],
-                     obj_prog_len=d.get("obj_prog_len", 0), blocks=blocks, **kw)
+                     obj_prog_len=d.get("obj_prog_len", 0), obj_prog_flags=d.get("obj_prog_flags", 0), blocks=blocks, **kw)
 
 
 def structure_signature(st):

@@ -244,6 +244,7 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   S.lin_l = cvt(desc->lin_l); S.lin_u = cvt(desc->lin_u);
   S.qa = cvt(desc->qa); S.lb0 = cvt(desc->lb0); S.ub0 = cvt(desc->ub0);
   S.objp = cvt(desc->obj_prog); S.obj_len = desc->obj_prog_len > 0 && desc->obj_prog.off >= 0 ? desc->obj_prog_len : 0;
+  S.obj_flags = desc->obj_prog_flags;
   if (S.obj_len && n > 16) { delete h; return fail(SCO_ERR_UNSUPPORTED, "non-quadratic objectives are limited to 16 variables"); }
   for (int g = 0; g < desc->n_groups; g++) {
     int bits = 0;

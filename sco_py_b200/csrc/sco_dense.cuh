@@ -398,6 +398,10 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
   const double *__restrict__ qg = field_ptr(S_, S_.q, a_.prm);
   const double *__restrict__ qag = field_ptr(S_, S_.qa, a_.prm);
   const int o_lb = w_.lb.off, o_ub = w_.ub.off, o_bb = w_.bb.off, o_msk = w_.msk.off, o_x = w_.x.off, o_s = w_.s.off;
+  // warm start (sco_settings.warm_start): the unscaled duals of this team's previous QP are parked in the generic
+  // working set's y arrays, which the dense solve does not use otherwise
+  const int o_yp = w_.yp.off, o_ys = w_.ys.off, o_yb = w_.yb.off;
+  const bool warm = a_.warm != 0, keep_duals = st_.warm_start != 0;
   const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sco_smem);
   const int half = tid >> 5;  // 0 / 1: the two warps split matrix rows
 
@@ -663,7 +667,42 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
   const uint32_t vb0 = sb + 8u * DL::Vb, vb1 = vb0 + 8u * VLD;
   const uint32_t my_out = 8u * (uint32_t)(publishes ? (rowwarp ? NP + lane : lane) : VLD - 1);
   const uint32_t my_chk = sb + 8u * ((rowwarp ? DL::Ys : DL::Xs) + lane);
-  if (publishes) sts_f64(vb0 + my_out, rowwarp ? -(rho * lo) * g : -u0);
+  double first_out = rowwarp ? -(rho * lo) * g : -u0;  // this lane's entry of (c, wp) for x = z = y = 0
+  if (warm) {
+    // OSQP's warm start (osqp_warm_start): x^ = D^-1 x, y^ = c E^-1 y, z^ = A^ x^ with the scaling of THIS QP; x, s and
+    // the duals are those the previous QP of this problem ended with.  The reference never warm-starts (it builds a
+    // new OSQP object per call, osqp_utils.py:195): opt-in, results agree to the QP tolerances, not bit for bit.
+    const double e0 = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 8)), e1 = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 9));
+    if (!rowwarp) {
+      if (act) {
+        X.p0 = lds_f64(sb + 8u * (o_x + lane)) / e1;        // / D
+        X.y0 = c * lds_f64(sb + 8u * (o_yb + lane)) / e0;   // c y / Eb
+        X.z0 = u1 * X.p0;
+      }
+      sts_f64(sb + 8u * (DL::Xs + lane), X.p0);
+    } else if (act) {
+      const double e2 = lds_f64(dense_la<NP, MP>(sb, true, lane, 10));
+      X.s = lds_f64(sb + 8u * (o_s + lane)) / e2;             // / Ds
+      X.ys = c * lds_f64(sb + 8u * (o_ys + lane)) / e1;       // c y / Es
+      X.zs = u2 * X.s;
+      X.y0 = c * (lds_f64(sb + 8u * (o_yp + lane)) / kd) / e0;  // the stored dual is the sum over the kd copies
+    }
+    __syncthreads();
+    if (rowwarp) {
+      const uint32_t jr = sb + 8u * (DL::Js + (lane < MP ? lane : 0) * LDJ), xs = sb + 8u * DL::Xs;
+      double t = 0.0;
+      for (int k = 0; k < NP; k++) t = fma(lds_f64(jr + 8u * k), lds_f64(xs + 8u * k), t);
+      if (act) X.z0 = t + u1 * X.s;
+      const double wpen = rho * X.z0 - X.y0;
+      const double rr = (sigma * X.s - u0) + u2 * (rho * X.zs - X.ys) + lo * wpen;
+      g = Mi * rr;
+      first_out = kd * wpen - (rho * lo) * g;
+    } else {
+      first_out = (sigma * X.p0 - u0) + u1 * (u2 * X.z0 - X.y0);
+    }
+    __syncthreads();
+  }
+  if (publishes) sts_f64(vb0 + my_out, first_out);
   int iter = 0, status = 0;
   bool checked = false;
   int next_check = chk ? chk : max_iter + 1;
@@ -798,6 +837,16 @@ __device__ __noinline__ QPResult dense_qp_solve(const DevStruct &S_, const DevSe
   if (act) {  // D / Ds are e1 / e2 of the lane-constant block
     if (rowwarp) sts_f64(sb + 8u * (o_s + lane), X.s * lds_f64(dense_la<NP, MP>(sb, true, lane, 10)));
     else sts_f64(sb + 8u * (o_x + lane), X.p0 * lds_f64(dense_la<NP, MP>(sb, false, lane, 9)));
+    if (keep_duals) {  // y = E y^ / c, for the next QP's warm start
+      const double e0 = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 8)), e1 = lds_f64(dense_la<NP, MP>(sb, rowwarp, lane, 9));
+      const double cinv = dense_sc<NP, MP>(sb, 5);
+      if (rowwarp) {
+        sts_f64(sb + 8u * (o_yp + lane), kd * e0 * X.y0 * cinv);
+        sts_f64(sb + 8u * (o_ys + lane), e1 * X.ys * cinv);
+      } else {
+        sts_f64(sb + 8u * (o_yb + lane), e0 * X.y0 * cinv);
+      }
+    }
   }
   __syncthreads();
   res.status = status;

@@ -104,7 +104,7 @@ struct DevStruct {
   DevField qa;         // AffExpr objective terms, summed (n): enters the QP with the weight of quirk C-4
   DevField lb0, ub0;   // user bounds of the scalar variables (n each): the closest-point QP honours them
   DevField objp;       // non-quadratic objective: stack program (1 row)
-  int obj_len, pad2_;  // its instruction count, 0 = none
+  int obj_len, obj_flags;  // its instruction count, 0 = none; bit 0: gradient by forward-mode differentiation
   // linear rows: CSR + CSC (entry index into lin_val / Als)
   const int *lin_rowptr, *lin_col, *lin_cptr, *lin_centry, *lin_crow;
   const double *lin_val;

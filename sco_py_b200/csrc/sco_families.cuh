@@ -136,16 +136,18 @@ __device__ void eval_fk7(const DevStruct &S, const DevBlock &B, const double *ta
 
 // ---- VM: rows given as stack programs (sco_py_b200/sym.py).  Program = m row offsets, then
 // (opcode, operand) pairs of doubles; opcodes END 0, PUSH_X 1, PUSH_C 2, ADD 3, SUB 4, MUL 5, DIV 6,
-// NEG 7, POWI 8, SQRT 9, LOG 10, EXP 11, SIN 12, COS 13.  Up to two variables may be replaced by
+// NEG 7, POWI 8, SQRT 9, LOG 10, EXP 11, SIN 12, COS 13, ABS 14, MIN 15, MAX 16, TEE 17 (copy the top of the stack
+// into temporary k), LOAD 18 (push temporary k).  Up to two variables may be replaced by
 // given values (the perturbed points of the finite differences) without copying x.
 #define SCO_VM_STACK 16
+#define SCO_VM_SLOTS 128  // a seven-link kinematic chain keeps ~100 rotation entries alive
 #define SCO_FD_JAC_STEP 5.477420592293901e-07    // eps^(1/2.5): numdifftools base step, first derivatives
 #define SCO_FD_HESS_STEP 9.843133202303692e-03  // eps^(1/7.8): second derivatives (oracle/shims/numdifftools)
 
 static __device__ __noinline__ double vm_eval(const double *prog, int m, int row, Sh x, int pi, double vi, int pj, double vj) {
   const double *ins = prog + m;
   int pc = (int)prog[row];
-  double stk[SCO_VM_STACK];
+  double stk[SCO_VM_STACK], slot[SCO_VM_SLOTS];
   int sp = 0;
   for (;;) {
     const int op = (int)ins[2 * pc];
@@ -167,11 +169,84 @@ static __device__ __noinline__ double vm_eval(const double *prog, int m, int row
       double v = 1.0;
       for (int k = (int)arg; k > 0; k--) v = v * a;
       stk[sp - 1] = v;
-    } else {
+    } else if (op <= 13) {
       const double a = stk[sp - 1];
       stk[sp - 1] = op == 9 ? sqrt(a) : op == 10 ? log(a) : op == 11 ? exp(a) : op == 12 ? sin(a) : cos(a);
+    } else if (op == 14) {
+      stk[sp - 1] = fabs(stk[sp - 1]);
+    } else if (op <= 16) {
+      const double b = stk[--sp], a = stk[sp - 1];
+      stk[sp - 1] = op == 15 ? (a <= b ? a : b) : (a >= b ? a : b);
+    } else if (op == 17) {
+      slot[(int)arg] = stk[sp - 1];
+    } else {
+      stk[sp++] = slot[(int)arg];
     }
   }
+  return stk[sp - 1];
+}
+
+// The same program in forward mode: value and d/dx_wrt, the exact counterpart of a user-supplied gradient
+// (Expr(f, grad), expr.py:86-88); SymExpr(..., analytic=True).  Rules as in sym.eval_program_dual.
+static __device__ __noinline__ double vm_eval_dual(const double *prog, int m, int row, Sh x, int wrt, double *dout) {
+  const double *ins = prog + m;
+  int pc = (int)prog[row];
+  double stk[SCO_VM_STACK], dsk[SCO_VM_STACK], slot[SCO_VM_SLOTS], dslot[SCO_VM_SLOTS];
+  int sp = 0;
+  for (;;) {
+    const int op = (int)ins[2 * pc];
+    const double arg = ins[2 * pc + 1];
+    pc++;
+    if (op == 0) break;
+    if (op == 1) {
+      const int i = (int)arg;
+      stk[sp] = x[i];
+      dsk[sp++] = i == wrt ? 1.0 : 0.0;
+    } else if (op == 2) {
+      stk[sp] = arg;
+      dsk[sp++] = 0.0;
+    } else if (op <= 6) {
+      --sp;
+      const double b = stk[sp], db = dsk[sp], a = stk[sp - 1], da = dsk[sp - 1];
+      if (op == 3) { stk[sp - 1] = a + b; dsk[sp - 1] = da + db; }
+      else if (op == 4) { stk[sp - 1] = a - b; dsk[sp - 1] = da - db; }
+      else if (op == 5) { stk[sp - 1] = a * b; dsk[sp - 1] = da * b + a * db; }
+      else { const double q = a / b; stk[sp - 1] = q; dsk[sp - 1] = (da - q * db) / b; }
+    } else if (op == 7) {
+      stk[sp - 1] = -stk[sp - 1];
+      dsk[sp - 1] = -dsk[sp - 1];
+    } else if (op == 8) {
+      const double a = stk[sp - 1];
+      const int k = (int)arg;
+      double v = 1.0, vm1 = 1.0;
+      for (int t = 0; t < k; t++) { vm1 = v; v = v * a; }
+      stk[sp - 1] = v;
+      dsk[sp - 1] = k > 0 ? k * vm1 * dsk[sp - 1] : 0.0;
+    } else if (op <= 13) {
+      const double a = stk[sp - 1], da = dsk[sp - 1];
+      if (op == 9) { const double v = sqrt(a); stk[sp - 1] = v; dsk[sp - 1] = da != 0.0 ? da / (2.0 * v) : 0.0; }  // sqrt of a constant 0 is flat
+      else if (op == 10) { stk[sp - 1] = log(a); dsk[sp - 1] = da / a; }
+      else if (op == 11) { const double v = exp(a); stk[sp - 1] = v; dsk[sp - 1] = v * da; }
+      else if (op == 12) { stk[sp - 1] = sin(a); dsk[sp - 1] = cos(a) * da; }
+      else { stk[sp - 1] = cos(a); dsk[sp - 1] = -sin(a) * da; }
+    } else if (op == 14) {
+      const double a = stk[sp - 1];
+      stk[sp - 1] = fabs(a);
+      if (!(a >= 0.0)) dsk[sp - 1] = -dsk[sp - 1];
+    } else if (op <= 16) {
+      --sp;
+      const double b = stk[sp], a = stk[sp - 1];
+      const bool keep_a = op == 15 ? a <= b : a >= b;
+      if (!keep_a) { stk[sp - 1] = b; dsk[sp - 1] = dsk[sp]; }
+    } else if (op == 17) {
+      slot[(int)arg] = stk[sp - 1];
+      dslot[(int)arg] = dsk[sp - 1];
+    } else {
+      stk[sp] = slot[(int)arg];
+      dsk[sp++] = dslot[(int)arg];
+    }
+  }
+  *dout = dsk[sp - 1];
   return stk[sp - 1];
 }
 
@@ -213,8 +288,17 @@ template <int TEAM>
 __device__ void eval_vm(const DevStruct &S, const DevBlock &B, const double *prog, Sh x, Sh f, double *Jout) {
   const int n = S.n, m = B.m;
   for (int r = threadIdx.x; r < m; r += TEAM) f[r] = vm_eval(prog, m, r, x, -1, 0.0, -1, 0.0);
-  if (Jout)
-    for (int e = threadIdx.x; e < m * n; e += TEAM) Jout[e] = vm_fd1(prog, m, e / n, x, e % n);
+  if (Jout) {
+    if (B.ipar[3]) {  // analytic: the program differentiated in forward mode (one pass per entry)
+      for (int e = threadIdx.x; e < m * n; e += TEAM) {
+        double d;
+        vm_eval_dual(prog, m, e / n, x, e % n, &d);
+        Jout[e] = d;
+      }
+    } else {
+      for (int e = threadIdx.x; e < m * n; e += TEAM) Jout[e] = vm_fd1(prog, m, e / n, x, e % n);
+    }
+  }
 }
 
 // Evaluate every block at x: fv[row] = f_row(x); if Jg != null also the stored Jacobian entries.

@@ -984,6 +984,39 @@ struct QPSolver {
     return status;
   }
 
+  // Warm start of the thread-per-entity loop (sco_settings.warm_start; OSQP's osqp_warm_start): the iterate arrays
+  // hold the UNSCALED x, s and duals the previous QP of this team ended with (solve() unscales them when the setting
+  // is on); x^ = D^-1 x, y^ = c E^-1 y, z^ = A^ x^ with the scaling of this QP.
+  __device__ __noinline__ void warm_init() {
+    SCO_QP_LOCALS
+    for (int j = tid; j < n; j += TEAM) {
+      const double xh = W_x[j] / W_D[j];
+      W_x[j] = xh;
+      W_zb[j] = W_bx[j] * xh;
+      W_yb[j] = c * W_yb[j] / W_Eb[j];
+    }
+    for (int i = tid; i < m_nl; i += TEAM)
+      for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) {
+        const int si = k2 * ms + i;
+        const double sh = W_s[si] / W_Ds[si];
+        W_s[si] = sh;
+        W_zs[si] = W_bs[si] * sh;
+        W_ys[si] = c * W_ys[si] / W_Es[si];
+      }
+    sync();
+    for (int r = tid; r < m_lin; r += TEAM) {
+      W_zl[r] = lin_row_dot(r, W_x);
+      W_yl[r] = c * W_yl[r] / W_El[r];
+    }
+    for (int i = tid; i < m_nl; i += TEAM) {
+      double ax = pen_row_dot(i, W_x) + W_sl[i] * W_s[i];
+      if (__ldg(S.row_eq + (i))) ax += W_sl[ms + i] * W_s[ms + i];
+      W_zp[i] = ax;
+      W_yp[i] = c * (W_yp[i] / a.kd) / W_Ep[i];  // the stored dual is the sum over the kd copies of the row
+    }
+    sync();
+  }
+
   // roles start on warp boundaries: ceil32(n) variable lanes, ceil32(m_lin) linear-row lanes, ceil32(m_nl) penalty-row lanes
   // ... and every row of A has at most SCO_EN entries, every column at most SCO_EH from linear and SCO_EH from
   // penalty rows (S.fast_ok, checked once by sco_create)
@@ -1012,14 +1045,17 @@ struct QPSolver {
     f.max_iter = this->st.max_iter; f.chk = this->st.check_termination; f.has_pen = m_nl != 0; f.m_nl = m_nl;
     f.sigma = this->st.sigma; f.alpha = this->st.alpha; f.kd = this->a.kd; f.cpi = this->c * this->a.pi;
     for (int e = tid; e < f.K3 * n; e += TEAM) wq.ps[e] = 0.0;  // segments beyond n contribute exact zeros
-    // ADMM starts from x = z = y = 0 (osqp_utils.py:195 builds a new OSQP object per call); fast_role reads its
-    // iterates from these arrays
+    // ADMM starts from x = z = y = 0 (osqp_utils.py:195 builds a new OSQP object per call) unless the opt-in warm
+    // start applies; fast_role reads its iterates from these arrays
+    if (this->a.warm) warm_init();
+    else {
     for (int j = tid; j < n; j += TEAM) { wq.x[j] = 0.0; wq.zb[j] = 0.0; wq.yb[j] = 0.0; }
     for (int r = tid; r < m_lin; r += TEAM) { wq.zl[r] = 0.0; wq.yl[r] = 0.0; }
     for (int i = tid; i < m_nl; i += TEAM) {
       wq.zp[i] = 0.0; wq.yp[i] = 0.0;
       wq.s[i] = 0.0; wq.zs[i] = 0.0; wq.ys[i] = 0.0;
       if (__ldg(this->S.row_eq + (i))) { wq.s[f.ms + i] = 0.0; wq.zs[f.ms + i] = 0.0; wq.ys[f.ms + i] = 0.0; }
+    }
     }
     // the dense variants read their operands in groups of four: pad wp / xt2 with zeros (the arrays behind them are
     // rewritten before they are read)
@@ -1249,6 +1285,15 @@ struct QPSolver {
     for (int j = tid; j < n; j += TEAM) w.x[j] *= w.D[j];
     for (int i = tid; i < m_nl; i += TEAM)
       for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) w.s[k2 * ms + i] *= w.Ds[k2 * ms + i];
+    if (st.warm_start) {  // duals too (y = E y^ / c), for the warm start of this team's next QP (warm_init)
+      const double ci = 1.0 / c;
+      for (int j = tid; j < n; j += TEAM) w.yb[j] *= w.Eb[j] * ci;
+      for (int r = tid; r < m_lin; r += TEAM) w.yl[r] *= w.El[r] * ci;
+      for (int i = tid; i < m_nl; i += TEAM) {
+        w.yp[i] *= a.kd * w.Ep[i] * ci;
+        for (int k2 = 0; k2 <= __ldg(S.row_eq + (i)); k2++) w.ys[k2 * ms + i] *= w.Es[k2 * ms + i] * ci;
+      }
+    }
     sync();
     res.status = status;
     res.iters = iter;

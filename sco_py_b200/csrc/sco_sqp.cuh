@@ -95,7 +95,10 @@ struct SqpSolver {
         w.Sm[i * n + j] = h; w.Sm[j * n + i] = h;
       }
     }
-    for (int j = tid; j < n; j += TEAM) w.xt[j] = vm_fd1(prog, 1, 0, xc, j);  // gradient
+    for (int j = tid; j < n; j += TEAM) {  // gradient: finite differences, or the program's own derivative
+      if (S.obj_flags & 1) { double d; vm_eval_dual(prog, 1, 0, xc, j, &d); w.xt[j] = d; }
+      else w.xt[j] = vm_fd1(prog, 1, 0, xc, j);
+    }
     sync();
     if (tid == 0) {  // smallest eigenvalue: cyclic Jacobi on the scratch copy (n <= 16)
       for (int sweep = 0; sweep < 50; sweep++) {
@@ -285,7 +288,9 @@ struct SqpSolver {
             sync();
             QPArgs a;
             a.prm = prm; a.Jg = Jg; a.pi = pi; a.kd = kd; a.wa = wa; a.use_pen = 1; a.closest = 0; a.has_hq = S.obj_len != 0;
-            a.warm = (st.warm_start && !first_qp) ? 1 : 0;
+            // warm_start 1: QPs of one trust-region loop (same J, b, weights; only the box moves); 2: every penalty QP
+            // after the problem's first one
+            a.warm = (st.warm_start == 1 && !first_qp) || (st.warm_start >= 2 && o.qp_solves > 1) ? 1 : 0;
             first_qp = false;
             // one thread looks at the queue and the team agrees on the answer (a per-thread read could
             // split the team at the moment the queue runs dry)

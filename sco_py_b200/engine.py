@@ -67,6 +67,7 @@ class Engine(object):
         cs.Q, cs.q, cs.c = _field(st.Q), _field(st.q), _field(st.c)
         cs.lin_l, cs.lin_u = _field(st.lin_l), _field(st.lin_u)
         cs.obj_prog, cs.obj_prog_len = _field(st.obj_prog), int(st.obj_prog_len)
+        cs.obj_prog_flags = int(getattr(st, "obj_prog_flags", 0))
         cs.qa, cs.lb0, cs.ub0 = _field(st.qa), _field(st.lb0), _field(st.ub0)
         if st.m_lin:
             cs.lin_rowptr = hold(st.lin_rowptr, np.int32)

@@ -395,28 +395,36 @@ class FK7Expr(DeviceFamilyExpr):
 
 
 class SymExpr(DeviceFamilyExpr):
-    """Rows written in the expression language of sco_py_b200.sym, over ALL n variables.  No analytic
-    derivatives: Jacobians (constraints) and gradient + Hessian (a non-quadratic objective,
-    expr.py:102-156) are finite-differenced with the numdifftools scheme, on the device by the VM family
-    and on the host by `Expr.grad` / `Expr.hess` -- exactly what the reference does with `Expr(f)`."""
+    """Rows written in the expression language of sco_py_b200.sym, over ALL n variables.
+
+    analytic=False (default): no analytic derivatives -- Jacobians (constraints) and gradient + Hessian (a
+    non-quadratic objective, expr.py:102-156) are finite-differenced with the numdifftools scheme, on the device by the
+    VM family and on the host by `Expr.grad` / `Expr.hess`: exactly what the reference does with `Expr(f)`.
+    analytic=True: the counterpart of `Expr(f, grad)` (expr.py:86-88): the program is differentiated in forward mode,
+    on the device (vm_eval_dual) and on the host (sym.jacobian); a non-quadratic objective keeps its numerical
+    Hessian, as in the reference when only `grad` is given (expr.py:102-109)."""
 
     family = FAM_VM
 
-    def __init__(self, rows, n):
+    def __init__(self, rows, n, analytic=False):
         self.n = int(n)
         self.rows = list(rows)
         self.m = len(self.rows)
+        self.analytic = bool(analytic)
         self.program, self.n_instr = sym.compile_rows(self.rows)
         ins = self.program[self.m:].reshape(-1, 2)
         used = ins[ins[:, 0] == sym.PUSH_X, 1]
         if used.size and (used.min() < 0 or used.max() >= self.n):  # the device would read past x
             raise ValueError("SymExpr over %d variables uses variable index %d" % (self.n, int(used.max())))
         self.jw = self.n
-        self.ipar = [self.n, self.m, self.n_instr, 0, 0, 0, 0, 0]
-        Expr.__init__(self, self._f, None)
+        self.ipar = [self.n, self.m, self.n_instr, int(self.analytic), 0, 0, 0, 0]
+        Expr.__init__(self, self._f, self._g if self.analytic else None)
 
     def _f(self, x):
         return sym.eval_program(self.program, self.m, np.asarray(x).ravel()).reshape(self.m, 1)
+
+    def _g(self, x):
+        return sym.jacobian(self.program, self.m, self.n, np.asarray(x).ravel())
 
     def params(self):
         return self.program

@@ -65,6 +65,7 @@ class Structure:
     shared: Optional[np.ndarray] = None           # shared block
     obj_prog: Field = field(default_factory=Field)  # non-quadratic objective: stack program (sym.py), 1 row
     obj_prog_len: int = 0                           # its instruction count (0 = none)
+    obj_prog_flags: int = 0                         # bit 0: gradient by forward-mode differentiation (SymExpr analytic=True)
     qa: Field = field(default_factory=Field)        # n: summed A rows of AffExpr objective terms (quirk C-4 weight in the QP)
     lb0: Field = field(default_factory=Field)       # n: user lower bounds of the scalar variables (closest-point QP)
     ub0: Field = field(default_factory=Field)       # n: user upper bounds

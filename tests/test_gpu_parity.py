@@ -336,3 +336,28 @@ def test_thread_per_entity_loop_matches_the_strided_loop(engines, name):
     xb, sb, ib = eng.qp_solve(params, _settings(force_generic=1), xref=x0, use_penalty=False, closest_point=True)
     assert np.array_equal(sa.cpu().numpy(), sb.cpu().numpy()) and np.array_equal(ia.cpu().numpy(), ib.cpu().numpy())
     assert np.abs(xa.cpu().numpy() - xb.cpu().numpy()).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CONFIGS])
+@pytest.mark.parametrize("level", [1, 2])
+def test_warm_start_mode_agrees_with_cold_start(engines, name, level):
+    """sco_settings.warm_start: QPs start from the previous QP's (x, y) -- level 1 inside one
+    trust-region loop (only l, u change between those QPs, solver.py:136-146), level 2 across the whole SQP.  The
+    reference never warm-starts (osqp_utils.py:195 builds a new OSQP object per call), so this is an opt-in mode judged
+    against the cold-start results of the same engine: every QP still ends on OSQP's termination criteria, the SQP
+    trajectories differ at that level."""
+    eng, st, params, x0 = engines[name]
+    cold = eng.solve_batch(params, x0, _settings())
+    warm = eng.solve_batch(params, x0, _settings(warm_start=level))
+    vc, vw = cold["verdict"].cpu().numpy(), warm["verdict"].cpu().numpy()
+    xc, xw = cold["x"].cpu().numpy(), warm["x"].cpu().numpy()
+    ic, iw = cold["stats"][:, 2].cpu().numpy().astype(float), warm["stats"][:, 2].cpu().numpy().astype(float)
+    same = vc == vw
+    rel = np.abs(xc - xw).max(axis=1) / np.maximum(1.0, np.abs(xc).max(axis=1))
+    print("warm_start=%d %s: verdicts equal %d/%d, rel |dx| median %.1e, ADMM iterations %.0f -> %.0f per problem" % (
+        level, name, same.sum(), same.size, np.median(rel[same]), ic.mean(), iw.mean()))
+    assert same.mean() >= 0.9
+    assert np.median(rel[same]) <= 1e-4
+    both = (vc == 1) & (vw == 1)
+    assert (warm["max_vio"].cpu().numpy()[both] <= 1e-4).all()  # converged means feasible, warm or cold
+    assert iw.sum() <= 1.05 * ic.sum()
