@@ -242,6 +242,12 @@ int sco_solve_batch_host(sco_handle *h, int64_t B, const double *params, const d
  * obj[B] = 0.5x'Qx + q'x + c.  Any output may be NULL. */
 int sco_convexify(sco_handle *h, int64_t B, const double *d_params, const double *d_x, double *d_f,
                   double *d_J, double *d_b, double *d_obj, void *stream);
+/* Same, plus the convex degree-2 model of the non-quadratic objective term (Expr.hess / _num_hess and
+ * Expr.convexify degree 2, expr.py:102-128,143-153): H+ = H - min(lambda_min, 0) I [B,n,n], A = grad - x'H+ [B,n],
+ * b = 0.5 x'H+x - grad.x + f [B].  Any output may be NULL; an error if the structure has no such term. */
+int sco_convexify_model(sco_handle *h, int64_t B, const double *d_params, const double *d_x, double *d_f,
+                        double *d_J, double *d_b, double *d_obj, double *d_H, double *d_g, double *d_c,
+                        void *stream);
 
 /* One penalty QP per problem:  min 0.5 x'sym(Q)x + q'x + pi*1's  s.t. lin rows, kdup copies of the
  * penalty rows (J.*mask) x -/+ s {<=,=} -b, lbx <= x <= ubx, s >= 0.   use_penalty=0 drops the

@@ -59,7 +59,7 @@ class CSettings(ctypes.Structure):
 
 EXPORTS = ["sco_last_error", "sco_default_settings", "sco_create", "sco_destroy", "sco_query",
            "sco_solve_batch", "sco_solve_batch_ordered", "sco_solve_batch_io", "sco_solve_batch_host",
-           "sco_solve_batch_host_async", "sco_solve_batch_host_groups", "sco_convexify", "sco_qp_solve",
+           "sco_solve_batch_host_async", "sco_solve_batch_host_groups", "sco_convexify", "sco_convexify_model", "sco_qp_solve",
            "sco_qp_solve_w", "sco_merit", "sco_probe_fp64"]
 
 _lib = None
@@ -97,6 +97,7 @@ def load():
     lib.sco_solve_batch_host_async.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(CSettings), c_vp,
                                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.sco_convexify.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.sco_convexify_model.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     lib.sco_qp_solve.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                  ctypes.c_int, ctypes.c_int, ctypes.POINTER(CSettings), c_vp, c_vp,
                                  c_vp, c_vp]

@@ -617,7 +617,14 @@ static unsigned stage_grid(sco_handle *h, int64_t B) {
 
 extern "C" int sco_convexify(sco_handle *h, int64_t B, const double *d_params, const double *d_x,
                              double *d_f, double *d_J, double *d_b, double *d_obj, void *stream) {
+  return sco_convexify_model(h, B, d_params, d_x, d_f, d_J, d_b, d_obj, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int sco_convexify_model(sco_handle *h, int64_t B, const double *d_params, const double *d_x,
+                                   double *d_f, double *d_J, double *d_b, double *d_obj, double *d_H, double *d_g,
+                                   double *d_c, void *stream) {
   if (!h || !d_params || !d_x) return fail(SCO_ERR_ARG, "null argument");
+  if ((d_H || d_g || d_c) && !h->S.obj_len) return fail(SCO_ERR_ARG, "the structure has no non-quadratic objective term");
   if (B <= 0) return SCO_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -629,7 +636,7 @@ extern "C" int sco_convexify(sco_handle *h, int64_t B, const double *d_params, c
     CUDA_TRY(cudaStreamWaitEvent(st, h->slot_done[slot], 0));
     scratch = h->Jscr[slot];
   }
-  ConvexifyArgs a = {(long long)B, d_params, d_x, d_f, d_J, d_b, d_obj, scratch};
+  ConvexifyArgs a = {(long long)B, d_params, d_x, d_f, d_J, d_b, d_obj, scratch, d_H, d_g, d_c};
   CUDA_TRY(h->gen_ops->prepare(h->carve_gen));
   h->gen_ops->convexify(stage_grid(h, B), h->smem_bytes, st, h->S, a);
   CUDA_TRY(cudaGetLastError());

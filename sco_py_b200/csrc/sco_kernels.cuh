@@ -83,7 +83,8 @@ template <int TEAM>
 __global__ void __launch_bounds__(TEAM)
 k_convexify(const __grid_constant__ DevStruct S, long long B, const double *__restrict__ params,
             const double *__restrict__ x, double *__restrict__ f, double *__restrict__ J,
-            double *__restrict__ bvec, double *__restrict__ obj, double *__restrict__ Jscr) {
+            double *__restrict__ bvec, double *__restrict__ obj, double *__restrict__ Jscr, double *__restrict__ Hq,
+            double *__restrict__ gq, double *__restrict__ cq) {
   QPW w;
   w.bind(S.L);
   const Sh xc = w.xc;
@@ -106,6 +107,12 @@ k_convexify(const __grid_constant__ DevStruct S, long long B, const double *__re
     if (obj) {
       const double ov = sq.objective();
       if (tid == 0) obj[b] = ov;
+    }
+    if (S.obj_len) {  // Expr.convexify degree 2 of the non-quadratic objective term (expr.py:143-153)
+      const int n = S.n;
+      if (Hq) for (int e = tid; e < n * n; e += TEAM) Hq[b * n * n + e] = w.Hq[e];
+      if (gq) for (int e = tid; e < n; e += TEAM) gq[b * n + e] = w.gq[e];
+      if (cq && tid == 0) cq[b] = w.Hq[n * n];
     }
     Team<TEAM>::sync();
   }

@@ -22,6 +22,7 @@ struct ConvexifyArgs {
   long long B;
   const double *params, *x;
   double *f, *J, *b, *obj, *Jscr;
+  double *Hq, *gq, *cq;  // degree-2 model of a non-quadratic objective term: H+ [B,n,n], linear term [B,n], constant [B]
 };
 struct QpStageArgs {
   long long B;

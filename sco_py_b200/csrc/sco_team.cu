@@ -87,7 +87,7 @@ void solve(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, cons
 }
 #if SCO_DK == 0
 void convexify(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, const ConvexifyArgs &a) {
-  k_convexify<T><<<grid, T, smem, st>>>(S, a.B, a.params, a.x, a.f, a.J, a.b, a.obj, a.Jscr);
+  k_convexify<T><<<grid, T, smem, st>>>(S, a.B, a.params, a.x, a.f, a.J, a.b, a.obj, a.Jscr, a.Hq, a.gq, a.cq);
 }
 #endif
 void qp(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, const DevSettings &d,

@@ -168,6 +168,17 @@ class Engine(object):
                                           _ptr(obj), self._stream()))
         return f, J, b, obj
 
+    def convexify_model(self, params, x):
+        """Degree-2 model of the non-quadratic objective term at x: (H+ [B,n,n], A [B,n], b [B])."""
+        params, x = self._dev(params), self._dev(x)
+        B = x.shape[0]
+        H = torch.empty((B, self.n, self.n), dtype=torch.float64, device=self.device)
+        g = torch.empty((B, self.n), dtype=torch.float64, device=self.device)
+        c = torch.empty(B, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.sco_convexify_model(self.h, B, _ptr(params), _ptr(x), None, None, None, None, _ptr(H),
+                                                _ptr(g), _ptr(c), self._stream()))
+        return H, g, c
+
     def qp_solve(self, params, settings, J=None, b=None, mask=None, lbx=None, ubx=None, pi=None,
                  kdup=None, xref=None, use_penalty=True, closest_point=False, wa=None):
         params = self._dev(params)

@@ -130,7 +130,9 @@ SYM_PROBLEMS = {
 }
 
 
-def build_sym(name, x0=None):
+def build_sym(name, x0=None, analytic=False):
+    """analytic=True: the functions come with their exact derivatives (Expr(f, grad), expr.py:86-88) instead of being
+    finite-differenced (the objective keeps its numerical Hessian, expr.py:102-109)."""
     x0_, x_true, Q, q, A_ineq, b_ineq, f, g, h = SYM_PROBLEMS[name]
     x0 = np.array(x0_ if x0 is None else x0, dtype=float).reshape(2, 1)
     prob = Prob()
@@ -140,14 +142,14 @@ def build_sym(name, x0=None):
     var = Variable(ov, value=x0)
     prob.add_var(var)
     prob.add_obj_expr(BoundExpr(QuadExpr(Q, q, np.zeros((1, 1))), var))
-    prob.add_obj_expr(BoundExpr(SymExpr([f if f is not None else sym.Sym.wrap(0.0)], 2), var))    # zerofunc
+    prob.add_obj_expr(BoundExpr(SymExpr([f if f is not None else sym.Sym.wrap(0.0)], 2, analytic=analytic), var))    # zerofunc
     if A_ineq is None:
         A_ineq, b_ineq = np.zeros((1, N)), np.zeros((1, 1))
     prob.add_cnt_expr(BoundExpr(LEqExpr(AffExpr(A_ineq, -b_ineq), np.zeros(b_ineq.shape)), var))
     g = g if g is not None else [sym.Sym.wrap(-1e5)]                                               # neginffunc
-    prob.add_cnt_expr(BoundExpr(LEqExpr(SymExpr(g, 2), np.zeros((len(g), 1))), var))
+    prob.add_cnt_expr(BoundExpr(LEqExpr(SymExpr(g, 2, analytic=analytic), np.zeros((len(g), 1))), var))
     h = h if h is not None else [sym.Sym.wrap(0.0)]                                                # zerofunc
-    prob.add_cnt_expr(BoundExpr(EqExpr(SymExpr(h, 2), np.zeros((len(h), 1))), var))
+    prob.add_cnt_expr(BoundExpr(EqExpr(SymExpr(h, 2, analytic=analytic), np.zeros((len(h), 1))), var))
     return prob, var, np.array(x_true)
 
 
@@ -203,4 +205,59 @@ def test_vm_family_values_and_fd_jacobians_match_the_oracle(name):
         r0 += blk.m
         e0 += blk.m * blk.jw
     assert abs(obj - pp.objective(pp.x)) <= 1e-12 * max(1.0, abs(obj))
+    eng.close()
+
+
+# ------------------------------------------------------------------ analytic derivatives (Expr(f, grad)) and the Hessian stage
+@pytest.mark.skipif(not ref_builder.reference_available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("name", ["prob1", "prob4", "prob7", "prob8"])
+def test_port_equals_the_unmodified_reference_with_analytic_gradients(name):
+    """The same functions handed to the unmodified reference as Expr(f, grad) with exact gradients."""
+    prob, var, x_true = build_sym(name, analytic=True)
+    st, params, x0, _ = batch.compile_batch([prob])
+    assert st.obj_prog_flags == 1 and all(b.ipar[3] == 1 for b in st.blocks)
+    a = sqp_port.solve(st, params[0], x0[0], solver=W.SOLVER_SETTINGS)
+    b = ref_builder.solve_with_reference(ref_builder.import_reference(), st, params[0], x0[0], solver=W.SOLVER_SETTINGS)
+    assert a["success"] == b["success"]
+    assert np.abs(a["x"] - b["x"]).max() <= 1e-7, (a["x"], b["x"])
+    assert np.allclose(b["x"], x_true, atol=5e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SYM_PROBLEMS))
+def test_device_reaches_the_reference_answers_with_analytic_gradients(name):
+    prob, var, x_true = build_sym(name, analytic=True)
+    st, params, x0, _ = batch.compile_batch([prob])
+    ref = sqp_port.solve(st, params[0], x0[0], solver=W.SOLVER_SETTINGS)
+    ok = _solver().solve(prob, method="penalty_sqp")
+    assert ok == ref["success"], name
+    assert np.allclose(var.get_value()[:, 0], x_true, atol=5e-4), (name, var.get_value()[:, 0])
+    assert np.abs(var.get_value()[:, 0] - ref["x"]).max() <= 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["prob1", "prob4", "prob7"])
+@pytest.mark.parametrize("analytic", [False, True])
+def test_objective_model_stage_matches_the_oracle(name, analytic):
+    """Stage level: numerical Hessian (central second differences, Richardson), smallest eigenvalue
+    by Jacobi sweeps, shift H - min(lambda, 0) I, A = grad - x'H, b = 0.5 x'Hx - grad.x + f on the device against the
+    oracle's Expr.hess / Expr.convexify(degree=2) restatement (expr.py:102-128,143-153), at points where the Hessian is
+    indefinite (the shift is active) and where it is not."""
+    from sco_py_b200.engine import Engine
+    rng = np.random.default_rng(11)
+    pts = np.vstack([np.array(SYM_PROBLEMS[name][0]), rng.uniform(-2.0, 2.0, (7, 2))])
+    probs = [build_sym(name, x0=p, analytic=analytic)[0] for p in pts]
+    st, params, x0, _ = batch.compile_batch(probs)
+    eng = Engine(st)
+    H, g, c = [t.cpu().numpy() for t in eng.convexify_model(params, x0)]
+    shifted = 0
+    for i in range(len(pts)):
+        pp = sqp_port.PortProblem(st, params[i], x0[i])
+        pp.convexify()
+        scale = max(1.0, np.abs(pp.Hq).max())
+        assert np.abs(H[i] - pp.Hq).max() <= 1e-6 * scale, (name, i, H[i], pp.Hq)
+        assert np.abs(g[i] - pp.aq).max() <= 1e-6 * max(1.0, np.abs(pp.aq).max()), (name, i)
+        assert abs(c[i] - pp.bq) <= 1e-6 * max(1.0, abs(pp.bq)), (name, i)
+        assert np.linalg.eigvalsh(H[i]).min() >= -1e-7 * scale  # convex after the shift
+        shifted += int(np.linalg.eigvalsh(pp.Hq).min() < 1e-9 * scale)
     eng.close()
