@@ -381,6 +381,9 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
     for (int i = 0; i < m_nl; i++) ok = ok && row_w[i] <= 8;
     for (int j = 0; j < n; j++) ok = ok && lcptr[j + 1] - lcptr[j] <= 4 && pc_ptr[j + 1] - pc_ptr[j] <= 4;
     S.fast_ok = ok ? 1 : 0;
+    bool narrow = true;
+    for (int j = 0; j < n; j++) narrow = narrow && P_cptr[j + 1] - P_cptr[j] <= 4;
+    S.p_narrow = narrow ? 1 : 0;
     bool dense = desc->m_lin == 0 && n <= 32 && m_nl > 0 && m_nl <= 48;
     for (int i = 0; i < m_nl; i++) dense = dense && row_w[i] == n;
     S.fast_dense = dense && !ok ? 1 : 0;

@@ -95,6 +95,7 @@ struct DevStruct {
   int sjnnz;           // padded Jacobian entries in shared memory
   int dense_kind;      // != 0: two-warp dense solve (sco_dense.cuh), index into its size table
   int fast_ok;         // rows of A with <= 8 entries, columns with <= 4 + 4: the thread-per-entity loop applies
+  int p_narrow;        // every column of the objective matrix's pattern has <= 4 entries (in-loop termination test)
   int fast_dense;      // dense penalty rows over n <= 32 variables, m_nl <= 48, no linear rows: its dense variant applies
   int s_bw;            // structural half-bandwidth of S = P + A'RA (max |i - j| over its pattern): the Gauss-Jordan
                        // sweep of pivot k only touches the leading (k + s_bw + 1)^2 block

@@ -669,7 +669,9 @@ struct QPSolver {
     int K3, j3, s3, c0, c1, p3_active;  // S^-1 rhs: column segment [c0, c1) of row j3
     int o_Sm, o_xt, o_xt2, o_ps, o_wl, o_wp;  // shared-memory offsets (doubles)
     int max_iter, chk, has_pen, m_nl;
+    int o_red, inline_test;  // the termination test inside the register loop (fast_role): reduction scratch, applicable?
     double sigma, alpha, kd, cpi;
+    double c, eps_abs, eps_rel, eps_pinf, eps_dinf;
   };
 
   // Hand-over of the iterates (and, at a test iteration, of the last step's deltas) to the shared-memory arrays that
@@ -750,6 +752,10 @@ struct QPSolver {
       double s1 = 0.0, zs1 = 0.0, ys1 = 0.0, sl1 = 0.0, bs1 = 0.0, rs1 = 1.0, rsi1 = 1.0, cd1 = 0.0, us1 = 0.0, hs1 = 0.0, g1 = 0.0;
       double s2 = 0.0, zs2 = 0.0, ys2 = 0.0, sl2 = 0.0, bs2 = 0.0, rs2 = 1.0, rsi2 = 1.0, cd2 = 0.0, us2 = 0.0, hs2 = 0.0, g2 = 0.0;
       double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, d4 = 0.0;  // deltas of the last iteration (certificates)
+      // scaling factors the in-loop termination test needs: variable Eb, D | linear row El | penalty row Ep, Es1, Ds1, Es2, Ds2
+      double k0 = 1.0, k1 = 1.0, k2s = 1.0, k3 = 1.0, k4 = 1.0;
+      double pq[4] = {0.0, 0.0, 0.0, 0.0};  // variable: its column of Psym (<= 4 entries) ...
+      int pa[4] = {f.o_ps, f.o_ps, f.o_ps, f.o_ps};  // ... and where the operands (D x)_k are published
       int eq = 0;
       {
         const QPW &wq = this->w;
@@ -758,6 +764,21 @@ struct QPSolver {
         if (ROLE == 0 && act) {
           const int j = id;
           x = wq.x[j]; zb = wq.zb[j]; yb = wq.yb[j];
+          k0 = wq.Eb[j]; k1 = wq.D[j];
+          if (!DENSE && f.inline_test) {
+            if (this->a.closest) { pq[0] = 2.0; pa[0] = f.o_xt + j; }
+            else if (this->Qg) {
+              const double *Qg_ = this->Qg;
+              const int p0 = __ldg(SS.P_cptr + (j)), p1 = __ldg(SS.P_cptr + (j + 1));
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                if (p0 + k < p1) {
+                  const int r = __ldg(SS.P_row + (p0 + k));
+                  pq[k] = 0.5 * (Qg_[r * n + j] + Qg_[j * n + r]);
+                  pa[k] = f.o_xt + r;
+                }
+            }
+          }
           qh = wq.qh[j]; bx = wq.bx[j]; rb = wq.rb[j]; rbi = 1.0 / rb; lb = wq.lb[j]; ub = wq.ub[j];
           int pl0 = 0, pl1 = 0, pp0 = 0, pp1 = 0;
           if (m_lin) { pl0 = __ldg(SS.lin_cptr + (j)); pl1 = __ldg(SS.lin_cptr + (j + 1)); }
@@ -781,6 +802,7 @@ struct QPSolver {
         } else if (ROLE == 1 && act) {
           const int r = id;
           z = wq.zl[r]; y = wq.yl[r];
+          k0 = wq.El[r];
           rr = wq.rl[r]; rri = 1.0 / rr; lo = wq.ll[r]; hi = wq.ul[r];
           const int p0 = __ldg(SS.lin_rowptr + (r)), p1 = __ldg(SS.lin_rowptr + (r + 1));
 #pragma unroll
@@ -790,6 +812,8 @@ struct QPSolver {
           const int i = id;
           eq = EQS ? __ldg(SS.row_eq + (i)) : 0;
           z = wq.zp[i]; y = wq.yp[i];
+          k0 = wq.Ep[i]; k1 = wq.Es[i]; k2s = wq.Ds[i];
+          if (EQS && eq) { k3 = wq.Es[ms + i]; k4 = wq.Ds[ms + i]; }
           rr = wq.rp[i]; rri = 1.0 / rr; lo = wq.lp[i]; hi = wq.up[i];
           mi11 = wq.Minv[3 * i]; mi12 = wq.Minv[3 * i + 1]; mi22 = wq.Minv[3 * i + 2];
           s1 = wq.s[i]; zs1 = wq.zs[i]; ys1 = wq.ys[i];
@@ -814,9 +838,9 @@ struct QPSolver {
       const bool p3_active = f.p3_active != 0;
       const int o_Sm = f.o_Sm, o_xt = f.o_xt, o_xt2 = f.o_xt2, o_ps = f.o_ps, o_wl = f.o_wl, o_wp = f.o_wp;
       const bool has_pen = f.has_pen != 0;
-      const int seg_end = next_check < max_iter ? next_check : max_iter;
-      // ---- iterations up to (and including) the next tested / last one: no call inside
-      while (iter < seg_end) {
+      // ---- iterations up to (and including) the next tested / last one that needs the out-of-line test: no call inside
+      bool leave = false, tested = false;
+      while (!leave) {
         iter++;
 #ifdef SCO_TIMING
         long long tph = clock64();
@@ -964,10 +988,113 @@ struct QPSolver {
           d0 = dy;
         }
         SCO_PH(3)
+        if (iter == next_check) {
+          next_check += chk;
+          tested = true;
+          leave = true;
+          if (!DENSE && f.inline_test && iter < max_iter) {
+            // ---- the termination test of check(), from the registers: same quantities, same arithmetic, one mixed
+            // reduction.  Only when it ends the solve -- or a certificate's first stage holds -- the iterates go to
+            // shared memory and check() itself decides (out of line: its code is cold, 17-36 k cycles a visit).
+            if (act) {
+              if (ROLE == 0) { sco_smem[o_xt2 + id] = x; sco_smem[o_xt + id] = k1 * x; }
+              else if (ROLE == 1) sco_smem[o_wl + id] = y;
+              else if (PEN) sco_smem[o_wp + id] = kd * y;
+            }
+            sync();
+            double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            double sums[2] = {0.0, 0.0};
+            if (act) {
+              if (ROLE == 1) {
+                double ax = 0.0;
+#pragma unroll
+                for (int k = 0; k < SCO_EN; k++) ax = fma(ec[k], sco_smem[ea[k]], ax);
+                const double ei = 1.0 / k0;
+                v[0] = fabs((ax - z) * ei); v[1] = fabs(z * ei); v[2] = fabs(ax * ei);
+                const double dy = proj_dy(d0, lo, hi);
+                v[7] = fabs(k0 * dy);
+                sums[0] += hi * fmax(dy, 0.0) + lo * fmin(dy, 0.0);
+              } else if (PEN) {
+                double ax = 0.0;
+#pragma unroll
+                for (int k = 0; k < SCO_EN; k++) ax = fma(ec[k], sco_smem[ea[k]], ax);
+                ax = ax + sl1 * s1;
+                if (EQS && eq) ax += sl2 * s2;
+                double ei = 1.0 / k0;
+                v[0] = fabs((ax - z) * ei); v[1] = fabs(z * ei); v[2] = fabs(ax * ei);
+                {
+                  const double dy = proj_dy(d0, lo, hi);
+                  v[7] = fabs(k0 * dy);
+                  sums[0] += kd * (hi * fmax(dy, 0.0) + lo * fmin(dy, 0.0));
+                }
+                {
+                  const double axs = bs1 * s1;
+                  ei = 1.0 / k1;
+                  v[0] = fmax(v[0], fabs((axs - zs1) * ei)); v[1] = fmax(v[1], fabs(zs1 * ei)); v[2] = fmax(v[2], fabs(axs * ei));
+                  const double di = 1.0 / k2s;
+                  const double aty = kd * sl1 * y + bs1 * ys1;
+                  v[3] = fabs((cd1 + aty) * di); v[4] = fabs(cd1 * di); v[5] = fabs(aty * di);
+                  const double dys = proj_dy(d2, 0.0, us1);
+                  v[7] = fmax(v[7], fabs(k1 * dys));
+                  sums[0] += us1 * fmax(dys, 0.0);
+                  v[8] = fabs(k2s * d1);
+                  sums[1] += cd1 * d1;
+                }
+                if (EQS && eq) {
+                  const double axs = bs2 * s2;
+                  ei = 1.0 / k3;
+                  v[0] = fmax(v[0], fabs((axs - zs2) * ei)); v[1] = fmax(v[1], fabs(zs2 * ei)); v[2] = fmax(v[2], fabs(axs * ei));
+                  const double di = 1.0 / k4;
+                  const double aty = kd * sl2 * y + bs2 * ys2;
+                  v[3] = fmax(v[3], fabs((cd2 + aty) * di)); v[4] = fmax(v[4], fabs(cd2 * di)); v[5] = fmax(v[5], fabs(aty * di));
+                  const double dys = proj_dy(d4, 0.0, us2);
+                  v[7] = fmax(v[7], fabs(k3 * dys));
+                  sums[0] += us2 * fmax(dys, 0.0);
+                  v[8] = fmax(v[8], fabs(k4 * d3));
+                  sums[1] += cd2 * d3;
+                }
+              } else if (ROLE == 0) {
+                const double ax = bx * x, ei = 1.0 / k0;
+                v[0] = fabs((ax - zb) * ei); v[1] = fabs(zb * ei); v[2] = fabs(ax * ei);
+                double px = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) px = fma(pq[k], sco_smem[pa[k]], px);
+                px *= f.c * k1;
+                double acc = 0.0, accp = 0.0;
+#pragma unroll
+                for (int k = 0; k < SCO_EH; k++) {
+                  acc = fma(ec[k], sco_smem[ea[k]], acc);
+                  accp = fma(ec[SCO_EH + k], sco_smem[ea[SCO_EH + k]], accp);
+                }
+                if (has_pen) acc += accp;
+                const double aty = acc + bx * yb;
+                const double di = 1.0 / k1;
+                v[3] = fabs((qh + px + aty) * di); v[4] = fabs(qh * di); v[5] = fabs(aty * di); v[6] = fabs(px * di);
+                const double dy = proj_dy(d1, lb, ub);
+                v[7] = fabs(k0 * dy);
+                sums[0] += ub * fmax(dy, 0.0) + lb * fmin(dy, 0.0);
+                v[8] = fabs(k1 * d0);
+                sums[1] += qh * d0;
+              }
+            }
+            Team<TEAM>::template reduce_mixed<9, 2>(v, sums, Sh{f.o_red});
+            const double cinv = 1.0 / f.c;
+            const double pri_res = v[0], dua_res = cinv * v[3];
+            bool go_on = !(pri_res > OSQP_INFTY || dua_res > OSQP_INFTY);
+            const double eps_p = f.eps_abs + f.eps_rel * fmax(v[1], v[2]);
+            const double eps_d = f.eps_abs + f.eps_rel * cinv * fmax(v[4], fmax(v[5], v[6]));
+            const bool prim_ok = pri_res < eps_p, dual_ok = dua_res < eps_d;
+            if (prim_ok && dual_ok) go_on = false;
+            if (!prim_ok && v[7] > f.eps_pinf && sums[0] < -f.eps_pinf * v[7]) go_on = false;
+            if (!dual_ok && v[8] > f.eps_dinf && sums[1] < -(f.c * f.eps_dinf * v[8])) go_on = false;
+            if (go_on) { leave = false; tested = false; }
+          }
+        } else if (iter >= max_iter) {
+          leave = true;
+        }
       }
-      // ---- iter == seg_end: the tested or the last iteration.  Iterates (+ deltas) -> shared memory, then the test.
-      const int can_check = iter == next_check;
-      if (can_check) next_check += chk;
+      // ---- the tested (and not waved through) or the last iteration.  Iterates (+ deltas) -> shared memory, then check().
+      const int can_check = tested ? 1 : 0;
 #ifdef SCO_TIMING
       long long tph = clock64();
 #endif
@@ -1044,6 +1171,10 @@ struct QPSolver {
     f.o_Sm = wq.Sm.off; f.o_xt = wq.xt.off; f.o_xt2 = wq.xt2.off; f.o_ps = wq.ps.off; f.o_wl = wq.wl.off; f.o_wp = wq.wp.off;
     f.max_iter = this->st.max_iter; f.chk = this->st.check_termination; f.has_pen = m_nl != 0; f.m_nl = m_nl;
     f.sigma = this->st.sigma; f.alpha = this->st.alpha; f.kd = this->a.kd; f.cpi = this->c * this->a.pi;
+    f.o_red = wq.red.off; f.c = this->c;
+    f.eps_abs = this->st.eps_abs; f.eps_rel = this->st.eps_rel; f.eps_pinf = this->st.eps_prim_inf; f.eps_dinf = this->st.eps_dual_inf;
+    // in-loop test: the objective matrix has at most four entries per column (or is the closest-point 2 I)
+    f.inline_test = (this->a.closest || this->S.p_narrow) && !this->a.has_hq;
     for (int e = tid; e < f.K3 * n; e += TEAM) wq.ps[e] = 0.0;  // segments beyond n contribute exact zeros
     // ADMM starts from x = z = y = 0 (osqp_utils.py:195 builds a new OSQP object per call) unless the opt-in warm
     // start applies; fast_role reads its iterates from these arrays
