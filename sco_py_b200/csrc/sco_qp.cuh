@@ -728,6 +728,8 @@ struct QPSolver {
   __device__ __noinline__ int fast_role(const FastCtx f, int &iter_out, bool &checked_out, QPResult &res) {
     constexpr bool PEN = ROLE == 2 || ROLE == 4, EQS = ROLE == 4;
     constexpr int NEC = DENSE ? (ROLE == 0 ? SCO_DM : SCO_DN) : SCO_EN;  // coefficient slots of this role
+    // the in-loop termination test costs ~20 registers: not at the 128-register budget of the 512-thread team
+    constexpr bool INL = !DENSE && TEAM <= 256;
     const int id = f.id, n = f.n;
     const bool act = f.act != 0;
     const double sigma = f.sigma, alpha = f.alpha, oma = 1.0 - f.alpha, kd = f.kd;
@@ -765,7 +767,7 @@ struct QPSolver {
           const int j = id;
           x = wq.x[j]; zb = wq.zb[j]; yb = wq.yb[j];
           k0 = wq.Eb[j]; k1 = wq.D[j];
-          if (!DENSE && f.inline_test) {
+          if (INL && f.inline_test) {
             if (this->a.closest) { pq[0] = 2.0; pa[0] = f.o_xt + j; }
             else if (this->Qg) {
               const double *Qg_ = this->Qg;
@@ -992,10 +994,11 @@ struct QPSolver {
           next_check += chk;
           tested = true;
           leave = true;
-          if (!DENSE && f.inline_test && iter < max_iter) {
+          if (INL && f.inline_test && iter < max_iter) {
             // ---- the termination test of check(), from the registers: same quantities, same arithmetic, one mixed
             // reduction.  Only when it ends the solve -- or a certificate's first stage holds -- the iterates go to
             // shared memory and check() itself decides (out of line: its code is cold, 17-36 k cycles a visit).
+            sync();  // P4b of the row roles still reads x~ from xt2
             if (act) {
               if (ROLE == 0) { sco_smem[o_xt2 + id] = x; sco_smem[o_xt + id] = k1 * x; }
               else if (ROLE == 1) sco_smem[o_wl + id] = y;
@@ -1088,6 +1091,7 @@ struct QPSolver {
             if (!prim_ok && v[7] > f.eps_pinf && sums[0] < -f.eps_pinf * v[7]) go_on = false;
             if (!dual_ok && v[8] > f.eps_dinf && sums[1] < -(f.c * f.eps_dinf * v[8])) go_on = false;
             if (go_on) { leave = false; tested = false; }
+            SCO_PH(4)
           }
         } else if (iter >= max_iter) {
           leave = true;
@@ -1194,6 +1198,7 @@ struct QPSolver {
     sync();
     if constexpr (TEAM <= 256) {  // the dense variants need ~200 registers: teams that have them
       if (!this->S.fast_ok) {
+        f.inline_test = 0;  // team-uniform: the idle role below is the <3, 0> instantiation and must not test alone
         if (role == 0) return fast_role<0, 1>(f, iter_out, checked_out, res);
         if (role == 2) return this->S.nsl == 2 ? fast_role<4, 1>(f, iter_out, checked_out, res) : fast_role<2, 1>(f, iter_out, checked_out, res);
         return fast_role<3, 0>(f, iter_out, checked_out, res);
