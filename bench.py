@@ -353,7 +353,9 @@ def time_config(args, name, B, steps, warmup, dev, local, rank, world, dist, sam
     st0 = W.GENERATORS[name](1)[0]
     h_params = torch.empty((B, st0.stride), dtype=torch.float64, pin_memory=True)
     h_x0 = torch.empty((B, st0.n), dtype=torch.float64, pin_memory=True)
-    st, _, _ = W.gen_batch(name, B, first=rank * B, out_params=h_params.numpy(), out_x0=h_x0.numpy())
+    # SCO_BENCH_SHARD=r (diagnostic, single GPU): solve the shard rank r of a multi-rank job would hold
+    shard = rank + int(os.environ.get("SCO_BENCH_SHARD", "0"))
+    st, _, _ = W.gen_batch(name, B, first=shard * B, out_params=h_params.numpy(), out_x0=h_x0.numpy())
     t_gen = time.time() - t_gen
     eng = Engine(st, device=local)
     settings = make_settings(solver=W.SOLVER_SETTINGS)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SCO_MAX_BLOCKS 8
+#define SCO_MAX_BLOCKS 16
 #define SCO_MAX_GROUPS 8
 
 /* nonlinear constraint families evaluated on device (closed set; the reference takes
@@ -252,7 +252,8 @@ int sco_convexify_model(sco_handle *h, int64_t B, const double *d_params, const 
 /* One penalty QP per problem:  min 0.5 x'sym(Q)x + q'x + pi*1's  s.t. lin rows, kdup copies of the
  * penalty rows (J.*mask) x -/+ s {<=,=} -b, lbx <= x <= ubx, s >= 0.   use_penalty=0 drops the
  * penalty rows and slacks; closest_point=1 replaces the objective by |x - xref|^2 (prob.py:369-412).
- * d_mask[B,m_nl] uint32 bit s <=> slot s of the row participates (NULL = all).
+ * d_mask[B,m_nl,W] uint32, W = ceil(widest stored Jacobian row / 32) (1 for rows of up to 32 entries):
+ * bit (s & 31) of word s >> 5 <=> slot s of the row participates (NULL = all).
  * Outputs: x[B,n_q] (user variables then slacks, unscaled), status[B], iters[B]. */
 int sco_qp_solve(sco_handle *h, int64_t B, const double *d_params, const double *d_J,
                  const double *d_b, const uint32_t *d_mask, const double *d_lbx, const double *d_ubx,

@@ -9,7 +9,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SCO_B200_LIB", os.path.join(PKG, "libsco_b200.so"))  # override: A/B runs of two builds
 
-MAX_BLOCKS = 8
+MAX_BLOCKS = 16
 MAX_GROUPS = 8
 
 c_i32, c_i64, c_dbl, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p

@@ -96,8 +96,9 @@ def compile_problem(prob):
             raise UnsupportedProblem("a non-quadratic objective must be a scalar SymExpr (sco_py_b200.sym) bound to "
                                      "a Variable that holds all scalar variables in QP order; black-box callables "
                                      "cannot run on the device and there is no CPU fallback")
-        if n > 16:
-            raise UnsupportedProblem("non-quadratic objectives are limited to 16 variables (serial eigenvalue shift)")
+        if n > 64:
+            raise UnsupportedProblem("non-quadratic objectives are limited to 64 variables (n x n Hessian model per "
+                                     "problem in shared memory, n^2 / 2 program evaluations per convexification)")
         if b.expr.n != n:
             raise UnsupportedProblem("the objective SymExpr is over %d variables, the problem has %d" % (b.expr.n, n))
         cp.obj_prog = b.expr

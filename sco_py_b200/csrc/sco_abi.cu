@@ -109,7 +109,7 @@ static void build_layout(DevStruct &S, int team) {
   L.Es = take(sl); L.gs = take(sl); L.hs = take(sl); L.rs = take(sl); L.dss = take(sl); L.dys = take(sl);
   L.Minv = take(3 * mp);
   L.red = take((std::max(team / 32, 8) + 1) * 16);  // one 16-double slot per warp + one for the combined results
-  L.msk = take((mp + 1) / 2);
+  L.msk = take((mp * S.mw + 1) / 2);
   L.stage = take(std::max((team / 32) * S.stage_per_warp, 100));
   L.Hq = take(S.obj_len ? n * n + 2 : 0); L.gq = take(S.obj_len ? n : 0);
   L.ps = take(4 * n);
@@ -245,7 +245,7 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   S.qa = cvt(desc->qa); S.lb0 = cvt(desc->lb0); S.ub0 = cvt(desc->ub0);
   S.objp = cvt(desc->obj_prog); S.obj_len = desc->obj_prog_len > 0 && desc->obj_prog.off >= 0 ? desc->obj_prog_len : 0;
   S.obj_flags = desc->obj_prog_flags;
-  if (S.obj_len && n > 16) { delete h; return fail(SCO_ERR_UNSUPPORTED, "non-quadratic objectives are limited to 16 variables"); }
+  if (S.obj_len && n > 64) { delete h; return fail(SCO_ERR_UNSUPPORTED, "non-quadratic objectives are limited to 64 variables"); }
   for (int g = 0; g < desc->n_groups; g++) {
     int bits = 0;
     if (desc->group_overlap)
@@ -256,6 +256,7 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   // ---- penalty rows
   std::vector<int> row_goff, row_soff, row_w, row_eq, row_gmask, jcol;
   int m_nl = 0, jnnz = 0, sj = 0, n_slack = 0, any_eq = 0, max_stage = 0;
+  int max_jw = 1;
   for (int bi = 0; bi < desc->n_blocks; bi++) {
     const sco_block_desc &b = desc->blocks[bi];
     DevBlock &d = S.blocks[bi];
@@ -275,7 +276,7 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
       jw = n;
       if (b.ipar[0] != n || b.ipar[1] != b.m || b.ipar[2] <= 0) { delete h; return fail(SCO_ERR_ARG, "VM: ipar must be {n, m, instructions}"); }
     } else { delete h; return fail(SCO_ERR_UNSUPPORTED, "unknown constraint family %d", b.family); }
-    if (jw > 32) { delete h; return fail(SCO_ERR_UNSUPPORTED, "Jacobian rows wider than 32 entries are not supported (n=%d)", n); }
+    max_jw = std::max(max_jw, jw);
     d.jw = jw;
     const int ldj = (jw % 2 == 0) ? jw + 1 : jw;
     for (int r = 0; r < b.m; r++) {
@@ -301,6 +302,7 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   S.m_nl = m_nl; S.jnnz = jnnz; S.sjnnz = sj; S.n_slack = n_slack; S.n_q = n + n_slack;
   S.nsl = any_eq ? 2 : 1;
   S.stage_per_warp = (max_stage + 1) & ~1;
+  S.mw = (max_jw + 31) / 32;
   // CSC over user variables of the stored Jacobian pattern
   std::vector<int> pc_ptr(n + 1, 0), pc_e, pc_r;
   {

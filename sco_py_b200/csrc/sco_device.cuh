@@ -9,7 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define SCO_DEV_MAX_BLOCKS 8
+#define SCO_DEV_MAX_BLOCKS 16
 #define SCO_DEV_MAX_GROUPS 8
 
 #define OSQP_INFTY 1e30
@@ -50,7 +50,7 @@ struct Layout {
   int s, Ds, sl, bs, zs, ys, Es, gs, hs, rs, dss, dys;
   int Minv;   // 3*m_nl
   int red;    // reduction scratch: 8 warps * 8 values
-  int msk;    // m_nl uint32 (counted in doubles, rounded up)
+  int msk;    // m_nl * mw uint32 (counted in doubles, rounded up)
   int stage;  // per-warp staging buffers for family evaluation
   int Hq, gq;  // degree-2 model of a non-quadratic objective: H+ (n*n, then b at [n*n]), linear term (n)
   int ps;     // partial sums of S^-1 rhs: 4 column segments x n (fast_loop, sco_qp.cuh)
@@ -100,6 +100,7 @@ struct DevStruct {
   int s_bw;            // structural half-bandwidth of S = P + A'RA (max |i - j| over its pattern): the Gauss-Jordan
                        // sweep of pivot k only touches the leading (k + s_bw + 1)^2 block
   int stage_per_warp;  // doubles
+  int mw;              // 32-bit words of a row's frozen-sparsity mask: ceil(widest row / 32), >= 1
   long long stride;
   DevField Q, q, c, lin_l, lin_u;
   DevField qa;         // AffExpr objective terms, summed (n): enters the QP with the weight of quirk C-4

@@ -137,11 +137,10 @@ k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st
       w.ub[j] = ubx ? ubx[b * n + j] : INFINITY;
       w.xs[j] = xref ? xref[b * n + j] : 0.0;
     }
-    if (use_pen)
-      for (int i = tid; i < ms; i += TEAM) {
-        w.bb[i] = bvec[b * ms + i];
-        w.msk[i] = mask ? mask[b * ms + i] : 0xffffffffu;
-      }
+    if (use_pen) {
+      for (int i = tid; i < ms; i += TEAM) w.bb[i] = bvec[b * ms + i];
+      for (int i = tid; i < ms * S.mw; i += TEAM) w.msk[i] = mask ? mask[b * ms * S.mw + i] : 0xffffffffu;
+    }
     Team<TEAM>::sync();
     QPArgs a;
     a.prm = params + b * S.stride;

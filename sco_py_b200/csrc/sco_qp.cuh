@@ -190,8 +190,8 @@ struct QPSolver {
     for (int r = tid; r < m_lin; r += TEAM) W_El[r] = 1.0;
     for (int i = tid; i < m_nl; i += TEAM) {
       const int so = __ldg(S.row_soff + (i)), go = __ldg(S.row_goff + (i)), wd = __ldg(S.row_w + (i));
-      const uint32_t mk = W_msk[i];
-      for (int k = 0; k < wd; k++) W_Js[so + k] = ((mk >> k) & 1u) ? a.Jg[go + k] : 0.0;
+      const int mo = i * SS.mw;
+      for (int k = 0; k < wd; k++) W_Js[so + k] = ((W_msk[mo + (k >> 5)] >> (k & 31)) & 1u) ? a.Jg[go + k] : 0.0;
       W_Ep[i] = 1.0;
       W_sl[i] = -1.0; W_bs[i] = 1.0; W_Ds[i] = 1.0; W_Es[i] = 1.0;
       if (__ldg(S.row_eq + (i))) {

@@ -100,34 +100,44 @@ struct SqpSolver {
       else w.xt[j] = vm_fd1(prog, 1, 0, xc, j);
     }
     sync();
-    if (tid == 0) {  // smallest eigenvalue: cyclic Jacobi on the scratch copy (n <= 16)
+    if (tid < 32) {
+      // smallest eigenvalue: cyclic Jacobi on the scratch copy, warp 0.  The rotations come in the serial (p, q) order
+      // and every element is computed by the formula of a one-thread sweep; the lanes only share the n elements of the
+      // two columns, then of the two rows, a rotation touches.
+      const int lane = tid;
       for (int sweep = 0; sweep < 50; sweep++) {
         double off = 0.0, dg = 0.0;
-        for (int p = 0; p < n; p++)
+        for (int p = lane; p < n; p += 32)
           for (int q = 0; q < n; q++) (p == q ? dg : off) += w.Sm[p * n + q] * w.Sm[p * n + q];
+        off = warp_sum(off); dg = warp_sum(dg);
         if (off <= 1e-30 * dg || off == 0.0) break;
         for (int p = 0; p < n - 1; p++)
           for (int q = p + 1; q < n; q++) {
-            const double apq = w.Sm[p * n + q];
+            const double apq = w.Sm[p * n + q], app = w.Sm[p * n + p], aqq = w.Sm[q * n + q];
+            __syncwarp();
             if (apq == 0.0) continue;
-            const double theta = (w.Sm[q * n + q] - w.Sm[p * n + p]) / (2.0 * apq);
+            const double theta = (aqq - app) / (2.0 * apq);
             const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
             const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
-            for (int k = 0; k < n; k++) {  // columns p, q
+            for (int k = lane; k < n; k += 32) {  // columns p, q
               const double akp = w.Sm[k * n + p], akq = w.Sm[k * n + q];
               w.Sm[k * n + p] = c * akp - sn * akq;
               w.Sm[k * n + q] = sn * akp + c * akq;
             }
-            for (int k = 0; k < n; k++) {  // rows p, q
+            __syncwarp();
+            for (int k = lane; k < n; k += 32) {  // rows p, q
               const double apk = w.Sm[p * n + k], aqk = w.Sm[q * n + k];
               w.Sm[p * n + k] = c * apk - sn * aqk;
               w.Sm[q * n + k] = sn * apk + c * aqk;
             }
+            __syncwarp();
           }
       }
-      double lam = w.Sm[0];
-      for (int p = 1; p < n; p++) lam = fmin(lam, w.Sm[p * n + p]);
-      w.Hq[n * n + 1] = lam;
+      if (lane == 0) {
+        double lam = w.Sm[0];
+        for (int p = 1; p < n; p++) lam = fmin(lam, w.Sm[p * n + p]);
+        w.Hq[n * n + 1] = lam;
+      }
     }
     sync();
     const double lam = w.Hq[n * n + 1];
@@ -203,10 +213,13 @@ struct SqpSolver {
         for (int k = 0; k < wd; k++) {
           const double jv = Jg[go + k];
           acc += jv * xc[__ldg(S.jcol_g + (go + k))];
-          if (jv != 0.0) mk |= (1u << k);
+          if (jv != 0.0) mk |= (1u << (k & 31));
+          if ((k & 31) == 31 || k == wd - 1) {  // one 32-bit word of the row's mask is complete
+            if (!mask_set) w.msk[i * S.mw + (k >> 5)] = st.freeze_sparsity ? mk : 0xffffffffu;
+            mk = 0;
+          }
         }
         w.bb[i] = -acc + w.fv[i] - (val ? val[r] : 0.0);
-        if (!mask_set) w.msk[i] = st.freeze_sparsity ? mk : 0xffffffffu;
       }
     }
     mask_set = true;

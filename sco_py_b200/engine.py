@@ -88,6 +88,8 @@ class Engine(object):
         _lib.check(self.lib.sco_query(self.h, q))
         (self.n, self.m_nl, self.n_slack, self.jnnz, self.n_q, self.smem_bytes, self.team,
          self.occupancy) = [int(v) for v in q]
+        # 32-bit words per penalty row of the frozen-sparsity mask passed to qp_solve (include/sco_b200.h)
+        self.mask_words = max(1, max([(b.jw + 31) // 32 for b in st.blocks], default=1))
 
     def close(self):
         if getattr(self, "h", None):
@@ -185,6 +187,8 @@ class Engine(object):
         B = params.shape[0]
         J, b, lbx, ubx, pi, xref, wa = [self._dev(a) for a in (J, b, lbx, ubx, pi, xref, wa)]
         mask = self._dev(mask, torch.int32) if mask is not None else None
+        if mask is not None and mask.numel() != B * self.m_nl * self.mask_words:
+            raise ValueError("mask must hold %d x %d x %d 32-bit words" % (B, self.m_nl, self.mask_words))
         kdup = self._dev(kdup, torch.int32) if kdup is not None else None
         nq = self.n_q if use_penalty else self.n
         xq = torch.empty((B, nq), dtype=torch.float64, device=self.device)

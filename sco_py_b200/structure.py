@@ -24,7 +24,7 @@ FAM_VM = 4         # stack program of sco_py_b200.sym, finite-difference Jacobia
 CNT_LEQ = 0        # LEqExpr  -> hinge penalty, 1 slack per row   (expr.py:353-371)
 CNT_EQ = 1         # EqExpr   -> abs penalty,   2 slacks per row  (expr.py:314-332)
 
-MAX_BLOCKS = 8
+MAX_BLOCKS = 16
 MAX_GROUPS = 8
 
 
