@@ -1,0 +1,40 @@
+"""Streaming regime of the generic ADMM loop: structures whose n x n system matrix does not fit in shared memory keep
+S^-1 in a per-team global workspace and read it once per iteration.  One penalty QP per problem (point robot over T
+time steps, n = 2 T), timed with CUDA events; the algorithmic traffic is iterations x n^2 x 8 bytes.
+    python profiles/stream_regime.py [T] [problems]"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from sco_py_b200 import workloads as W
+from sco_py_b200.engine import Engine, make_settings
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 120
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 592
+st, params, x0 = W.gen_point_robot(B, T=T)
+eng = Engine(st)
+s = make_settings(solver=W.SOLVER_SETTINGS)
+f, J, b, _ = eng.convexify(params, x0)
+args = dict(J=J, b=b, lbx=x0 - 1.0, ubx=x0 + 1.0, pi=np.full(B, 10.0), kdup=np.full(B, 1, np.int32))
+p_dev = torch.as_tensor(params).cuda()
+for _ in range(2):
+    xq, status, iters = eng.qp_solve(p_dev, s, **args)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+xq, status, iters = eng.qp_solve(p_dev, s, **args)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1)
+it = iters.cpu().numpy().astype(np.float64)
+byt = it.sum() * st.n * st.n * 8.0
+peak = None
+try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+except Exception:
+    pass
+print(json.dumps({"T": T, "n": st.n, "m_nl": st.m_nl, "problems": B, "team": eng.team, "smem_bytes": eng.smem_bytes,
+                  "S_bytes_per_team": 8 * st.n * st.n, "workspace_all_teams_MB": 8e-6 * st.n * st.n * 148 * eng.occupancy,
+                  "ms": ms, "admm_iters_total": it.sum(), "iters_mean": it.mean(), "status_counts": np.unique(status.cpu().numpy(), return_counts=True)[1].tolist(),
+                  "us_per_iteration_per_team": 1e3 * ms * 148 * eng.occupancy / it.sum(),
+                  "stream_GBps": byt / ms * 1e-6, "hbm_peak_GBps": peak,
+                  "frac_of_hbm_peak": (byt / ms * 1e-6 / peak) if peak else None}))

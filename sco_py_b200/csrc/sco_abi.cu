@@ -97,7 +97,7 @@ static void build_layout(DevStruct &S, int team) {
     return o;
   };
   const int n = S.n, ml = S.m_lin, mp = S.m_nl, sl = S.nsl * S.m_nl;
-  L.Js = take(S.sjnnz); L.S = take(n * n); L.Als = take(S.nnz_lin);
+  L.Js = take(S.sjnnz); L.S = take(S.sws ? 0 : n * n); L.Als = take(S.nnz_lin);
   L.x = take(n); L.xt = take(n); L.xt2 = take(n + 4); L.qh = take(n); L.D = take(n); L.bx = take(n);  // xt2, wp: + 4 = zero padding
   L.rb = take(n); L.lb = take(n); L.ub = take(n); L.zb = take(n); L.yb = take(n); L.Eb = take(n);
   L.dxv = take(n); L.dyb = take(n); L.xs = take(n);
@@ -414,6 +414,12 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
     build_layout(S, team);
     h->smem_bytes = (size_t)(S.L.total + ((n + 1) & ~1)) * sizeof(double);
     if (h->smem_bytes <= (size_t)prop.sharedMemPerBlockOptin) break;
+    if (!S.sws && !S.dense_kind && !S.obj_len) {
+      // the n x n matrix S (and its inverse) moves to a global workspace per resident team: the ADMM loop streams it
+      // from L2 / HBM in every iteration (strided loop only); everything else stays in shared memory
+      S.sws = n * n;
+      continue;
+    }
     sco_destroy(h);
     return fail(SCO_ERR_UNSUPPORTED, "problem working set (%zu B) exceeds shared memory per block (%zu B)",
                 h->smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
@@ -439,7 +445,7 @@ extern "C" int sco_create(const sco_structure_desc *desc, int device, sco_handle
   bool ok = cudaMalloc(&h->counter, sco_handle::NSLOT * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMalloc(&h->order_err, sco_handle::NSLOT * sizeof(int)) == cudaSuccess;
   for (int k = 0; k < sco_handle::NSLOT && ok; k++)
-    ok = cudaMalloc(&h->Jscr[k], std::max<size_t>(h->Jscr_ctas * std::max(jnnz, 1), 1) * sizeof(double)) == cudaSuccess &&
+    ok = cudaMalloc(&h->Jscr[k], std::max<size_t>(h->Jscr_ctas * (size_t)std::max(jnnz + S.sws, 1), 1) * sizeof(double)) == cudaSuccess &&
          cudaEventCreateWithFlags(&h->slot_done[k], cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < sco_handle::NSTG && ok; k++)
     ok = cudaEventCreateWithFlags(&h->stg[k].done, cudaEventDisableTiming) == cudaSuccess;
@@ -673,10 +679,17 @@ extern "C" int sco_qp_solve_w(sco_handle *h, int64_t B, const double *d_params, 
   cudaStream_t st = (cudaStream_t)stream;
   DevSettings d = to_dev(s);
   QpStageArgs a = {(long long)B, d_params, d_J, d_b, d_mask, d_lbx, d_ubx, d_pi, d_kdup, d_wa, d_xref,
-                   use_penalty, closest_point, d_xq, d_status, d_iters};
+                   use_penalty, closest_point, d_xq, d_status, d_iters, nullptr};
+  int slot = -1;
+  if (h->S.sws) {  // S lives in a launch slot's scratch: take the slot like a solve does
+    slot = (int)(h->next_slot++ % sco_handle::NSLOT);
+    CUDA_TRY(cudaStreamWaitEvent(st, h->slot_done[slot], 0));
+    a.scr = h->Jscr[slot];
+  }
   CUDA_TRY(h->ops->prepare(h->carve_ops));
   h->ops->qp(stage_grid(h, B), h->smem_bytes, st, h->S, d, a);
   CUDA_TRY(cudaGetLastError());
+  if (slot >= 0) CUDA_TRY(cudaEventRecord(h->slot_done[slot], st));
   return SCO_OK;
 }
 

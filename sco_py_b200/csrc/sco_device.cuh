@@ -100,6 +100,8 @@ struct DevStruct {
   int s_bw;            // structural half-bandwidth of S = P + A'RA (max |i - j| over its pattern): the Gauss-Jordan
                        // sweep of pivot k only touches the leading (k + s_bw + 1)^2 block
   int stage_per_warp;  // doubles
+  int sws;             // != 0: n * n doubles of S live in the team's global workspace (behind its Jacobian scratch),
+                       // not in shared memory: structures too large for one SM's shared memory otherwise
   int mw;              // 32-bit words of a row's frozen-sparsity mask: ceil(widest row / 32), >= 1
   long long stride;
   DevField Q, q, c, lin_l, lin_u;
@@ -305,6 +307,7 @@ struct QPW {
   Sh Hq, gq;
   Sh ps;
   Sh xc;  // current SQP iterate, n doubles appended after the layout
+  double *Sg;  // S in global memory (DevStruct::sws), else null; set by the kernel after bind()
 
   __device__ __forceinline__ void bind(const Layout &L) {
     Js = Sh{L.Js}; Sm = Sh{L.S}; Als = Sh{L.Als};
@@ -324,5 +327,6 @@ struct QPW {
     Hq = Sh{L.Hq}; gq = Sh{L.gq};
     ps = Sh{L.ps};
     xc = Sh{L.total};
+    Sg = nullptr;
   }
 };

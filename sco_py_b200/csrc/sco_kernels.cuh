@@ -41,7 +41,8 @@ k_solve(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings
   QPW w;
   w.bind(S.L);
   const Sh xc = w.xc;  // n doubles appended after the layout
-  double *Jg = Jscr + (size_t)blockIdx.x * S.jnnz;
+  double *Jg = Jscr + (size_t)blockIdx.x * (S.jnnz + S.sws);
+  if (S.sws) w.Sg = Jg + S.jnnz;
   const int tid = threadIdx.x;
   while (true) {
     if (tid == 0) next = (long long)atomicAdd(counter, 1ull);
@@ -126,9 +127,10 @@ k_qp(const __grid_constant__ DevStruct S, const __grid_constant__ DevSettings st
      const double *__restrict__ pi, const int *__restrict__ kdup, const double *__restrict__ wa,
      const double *__restrict__ xref,
      int use_pen, int closest, double *__restrict__ xq, int *__restrict__ status,
-     int *__restrict__ iters) {
+     int *__restrict__ iters, double *__restrict__ scr) {
   QPW w;
   w.bind(S.L);
+  if (S.sws) w.Sg = scr + (size_t)blockIdx.x * (S.jnnz + S.sws) + S.jnnz;
   const int tid = threadIdx.x;
   const int n = S.n, ms = S.m_nl;
   for (long long b = blockIdx.x; b < B; b += gridDim.x) {

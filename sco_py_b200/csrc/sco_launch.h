@@ -35,6 +35,7 @@ struct QpStageArgs {
   int use_pen, closest;
   double *xq;
   int *status, *iters;
+  double *scr;  // a launch slot's scratch (DevStruct::sws: S of every team lives there), else null
 };
 struct MeritArgs {
   long long B;

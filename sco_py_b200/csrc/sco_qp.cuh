@@ -97,6 +97,16 @@ struct QPSolver {
   //                       rows (vp; the caller folds the multiplicity kd into vp); bound row by the caller
   //   lin_row_dot / pen_row_dot   one row of A times a variable-space vector
   //   pcol_norm(j)        column j of c D |Psym| D
+// S = P + sigma I + A'RA and its inverse: in shared memory (W_Sm), or -- for structures whose n x n matrix does not fit
+// next to the rest of the working set (DevStruct::sws != 0) -- in the team's global workspace w.Sg (L2 / HBM)
+// SM_GLOBAL: which of the two, as the expanding function knows it (a template parameter in the setup functions)
+#define SM_GLOBAL (w.Sg != nullptr)
+#define SM_LD(i) (SM_GLOBAL ? w.Sg[i] : W_Sm[i])
+#define SM_ST(i, v)              \
+  do {                           \
+    if (SM_GLOBAL) w.Sg[i] = (v); \
+    else W_Sm[i] = (v);          \
+  } while (0)
 #define SCO_QP_LOCALS                                                                                       \
   const DevStruct &SS = this->S;                                                                            \
   const QPW w = this->w; /* offsets as individual scalars: registers, not a struct in local memory */        \
@@ -151,11 +161,11 @@ struct QPSolver {
   /* column j of c D |Psym| D over the pattern of Psym (closest point: 2 I; objective model: dense) */        \
   auto pcol_norm = [&](int j) -> double {                                                                   \
     double cp = 0.0;                                                                                        \
-    if (a.closest) cp = W_D[j] * fabs(W_Sm[j * n + j]);                                                     \
-    else if (a.has_hq) { for (int i = 0; i < n; i++) cp = fmax(cp, W_D[i] * fabs(W_Sm[i * n + j])); }       \
+    if (a.closest) cp = W_D[j] * fabs(SM_LD(j * n + j));                                                     \
+    else if (a.has_hq) { for (int i = 0; i < n; i++) cp = fmax(cp, W_D[i] * fabs(SM_LD(i * n + j))); }       \
     else for (int p = __ldg(S.P_cptr + (j)); p < __ldg(S.P_cptr + (j + 1)); p++) {                              \
       const int i = __ldg(S.P_row + (p));                                                                     \
-      cp = fmax(cp, W_D[i] * fabs(W_Sm[i * n + j]));                                                        \
+      cp = fmax(cp, W_D[i] * fabs(SM_LD(i * n + j)));                                                      \
     }                                                                                                       \
     return cp * c * W_D[j];                                                                                 \
   };                                                                                                        \
@@ -174,11 +184,14 @@ struct QPSolver {
 
   // ================================================================== setup
   // expects (unscaled): W_lb/W_ub bounds on x, W_bb = b, W_msk, W_xs (closest point target)
+#undef SM_GLOBAL
+#define SM_GLOBAL SG  // compile-time in the two setup functions: no test per matrix element
+  template <bool SG>
   __device__ __noinline__ void load_and_scale() {
     SCO_QP_LOCALS
     const double *qg = field_ptr(SS, SS.q, a.prm), *qag = field_ptr(SS, SS.qa, a.prm);
     const double *llg = field_ptr(SS, SS.lin_l, a.prm), *ulg = field_ptr(SS, SS.lin_u, a.prm);
-    for (int e = tid; e < n * n; e += TEAM) W_Sm[e] = psym(e / n, e % n);
+    for (int e = tid; e < n * n; e += TEAM) SM_ST(e, psym(e / n, e % n));
     for (int j = tid; j < n; j += TEAM) {
       W_qh[j] = a.closest ? -2.0 * W_xs[j]
                           : (qg ? qg[j] : 0.0) + (qag ? a.wa * qag[j] : 0.0) + (a.has_hq ? W_gq[j] : 0.0);
@@ -296,6 +309,8 @@ struct QPSolver {
     this->c = c;
     sync();
   }
+#undef SM_GLOBAL
+#define SM_GLOBAL (w.Sg != nullptr)
 
   __device__ void set_rho() {
     SCO_QP_LOCALS
@@ -313,6 +328,9 @@ struct QPSolver {
 
   // S = Psym^ + sigma I + A_x' R A_x - slack Schur terms, then S <- S^-1 (in place).
   // `reload`: Sm does not hold the unscaled Psym any more (rho update) -> fetch it again.
+#undef SM_GLOBAL
+#define SM_GLOBAL SG
+  template <bool SG>
   __device__ __noinline__ void assemble_and_invert(bool reload) {
     SCO_QP_LOCALS
     const double sigma = st.sigma;
@@ -342,10 +360,10 @@ struct QPSolver {
     }
     for (int e = tid; e < n * n; e += TEAM) {
       const int i = e / n, j = e % n;
-      const double pv = reload ? psym(i, j) : W_Sm[e];
+      const double pv = reload ? psym(i, j) : SM_LD(e);
       double v = c * W_D[i] * pv * W_D[j];
       if (i == j) v += sigma + W_rb[j] * W_bx[j] * W_bx[j];
-      W_Sm[e] = v;
+      SM_ST(e, v);
     }
     sync();
     for (int j = tid; j < n; j += TEAM) {
@@ -353,8 +371,10 @@ struct QPSolver {
         for (int p = __ldg(S.lin_cptr + (j)); p < __ldg(S.lin_cptr + (j + 1)); p++) {
           const int r = __ldg(S.lin_crow + (p));
           const double f = W_rl[r] * W_Als[__ldg(S.lin_centry + (p))];
-          for (int q2 = __ldg(S.lin_rowptr + (r)); q2 < __ldg(S.lin_rowptr + (r + 1)); q2++)
-            W_Sm[__ldg(S.lin_col + (q2)) * n + j] += f * W_Als[q2];
+          for (int q2 = __ldg(S.lin_rowptr + (r)); q2 < __ldg(S.lin_rowptr + (r + 1)); q2++) {
+            const int e2 = __ldg(S.lin_col + (q2)) * n + j;
+            SM_ST(e2, SM_LD(e2) + f * W_Als[q2]);
+          }
         }
       }
       if (m_nl) {
@@ -362,7 +382,10 @@ struct QPSolver {
           const int r = __ldg(S.pc_r + (p));
           const double f = W_wp[r] * W_Js[__ldg(S.pc_e + (p))];
           const int so = __ldg(S.row_soff + (r)), go = __ldg(S.row_goff + (r)), wd = __ldg(S.row_w + (r));
-          for (int k = 0; k < wd; k++) W_Sm[__ldg(S.jcol_g + (go + k)) * n + j] += f * W_Js[so + k];
+          for (int k = 0; k < wd; k++) {
+            const int e2 = __ldg(S.jcol_g + (go + k)) * n + j;
+            SM_ST(e2, SM_LD(e2) + f * W_Js[so + k]);
+          }
         }
       }
     }
@@ -374,10 +397,10 @@ struct QPSolver {
     const int bw = SS.s_bw;
     for (int k = 0; k < n; k++) {
       const int mk = (k + bw + 1) < n ? (k + bw + 1) : n;
-      const double d = 1.0 / W_Sm[k * n + k];
+      const double d = 1.0 / SM_LD(k * n + k);
       for (int j = tid; j < mk; j += TEAM) {
-        W_xt[j] = W_Sm[k * n + j] * d;
-        W_xt2[j] = W_Sm[j * n + k];
+        W_xt[j] = SM_LD(k * n + j) * d;
+        W_xt2[j] = SM_LD(j * n + k);
       }
       sync();
       int i = tid / mk, j = tid - i * mk;
@@ -387,8 +410,8 @@ struct QPSolver {
         double v;
         if (i == k) v = (j == k) ? d : W_xt[j];
         else if (j == k) v = -W_xt2[i] * d;
-        else v = W_Sm[e] - W_xt2[i] * W_xt[j];
-        W_Sm[e] = v;
+        else v = SM_LD(e) - W_xt2[i] * W_xt[j];
+        SM_ST(e, v);
         j += dj;
         i += di;
         if (j >= mk) { j -= mk; i++; }
@@ -396,6 +419,9 @@ struct QPSolver {
       sync();
     }
   }
+
+#undef SM_GLOBAL
+#define SM_GLOBAL (w.Sg != nullptr)
 
   // ================================================================== termination
   // Returns a terminal status or 0.  Scratch: xt (D.*x), wp (kd*yp).  sc[] receives the scaled
@@ -1152,7 +1178,7 @@ struct QPSolver {
   // ... and every row of A has at most SCO_EN entries, every column at most SCO_EH from linear and SCO_EH from
   // penalty rows (S.fast_ok, checked once by sco_create)
   __device__ __forceinline__ bool fast_fits() const {
-    return (S.fast_ok || (S.fast_dense && m_lin == 0)) && ((n + 31) & ~31) + ((m_lin + 31) & ~31) + ((m_nl + 31) & ~31) <= TEAM;
+    return !S.sws && (S.fast_ok || (S.fast_dense && m_lin == 0)) && ((n + 31) & ~31) + ((m_lin + 31) & ~31) + ((m_nl + 31) & ~31) <= TEAM;
   }
 
   __device__ __noinline__ int fast_loop(int &iter_out, bool &checked_out, QPResult &res) {
@@ -1273,6 +1299,19 @@ struct QPSolver {
         // shared-memory round trip: 28 cycles per term)
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
         int k = 0;
+        if (w.Sg) {  // S^-1 streamed from this team's global workspace (coalesced over j; same chains, same order)
+          const double *Sg = w.Sg + j;
+#pragma unroll 4
+          for (; k + 3 < n; k += 4) {
+            const double s0 = __ldcg(Sg + (size_t)k * n), s1 = __ldcg(Sg + (size_t)(k + 1) * n),
+                         s2 = __ldcg(Sg + (size_t)(k + 2) * n), s3 = __ldcg(Sg + (size_t)(k + 3) * n);
+            acc0 = fma(s0, W_xt[k], acc0);
+            acc1 = fma(s1, W_xt[k + 1], acc1);
+            acc2 = fma(s2, W_xt[k + 2], acc2);
+            acc3 = fma(s3, W_xt[k + 3], acc3);
+          }
+          for (; k < n; k++) acc0 = fma(__ldcg(Sg + (size_t)k * n), W_xt[k], acc0);
+        } else {
 #pragma unroll 2
         for (; k + 3 < n; k += 4) {
           const double s0 = W_Sm[k * n + j], s1 = W_Sm[(k + 1) * n + j], s2 = W_Sm[(k + 2) * n + j], s3 = W_Sm[(k + 3) * n + j];
@@ -1282,6 +1321,7 @@ struct QPSolver {
           acc3 = fma(s3, W_xt[k + 3], acc3);
         }
         for (; k < n; k++) acc0 = fma(W_Sm[k * n + j], W_xt[k], acc0);
+        }
         acc0 += acc2;
         acc1 += acc3;
         const double xtil = acc0 + acc1;
@@ -1353,7 +1393,7 @@ struct QPSolver {
             this->rho = rn;
             set_rho();
             rho = this->rho;
-            assemble_and_invert(true);
+            if (w.Sg) assemble_and_invert<true>(true); else assemble_and_invert<false>(true);
           }
         }
         sync();
@@ -1379,13 +1419,13 @@ struct QPSolver {
 #ifdef SCO_TIMING
     const long long t_begin = clock64();
 #endif
-    load_and_scale();
+    if (w.Sg) load_and_scale<true>(); else load_and_scale<false>();
 #ifdef SCO_TIMING
     const long long t_scaled = clock64();
 #endif
     rho = st.rho;
     set_rho();
-    assemble_and_invert(false);
+    if (w.Sg) assemble_and_invert<true>(false); else assemble_and_invert<false>(false);
     QPResult res;
     res.status = 0; res.iters = 0; res.pri_res = 0.0; res.dua_res = 0.0;
 #ifdef SCO_TIMING

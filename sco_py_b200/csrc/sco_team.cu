@@ -93,7 +93,7 @@ void convexify(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, 
 void qp(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, const DevSettings &d,
         const QpStageArgs &a) {
   k_qp<T, DK><<<grid, T, smem, st>>>(S, d, a.B, a.params, a.J, a.b, a.mask, a.lbx, a.ubx, a.pi, a.kdup, a.wa, a.xref,
-                                 a.use_pen, a.closest, a.xq, a.status, a.iters);
+                                 a.use_pen, a.closest, a.xq, a.status, a.iters, a.scr);
 }
 #if SCO_DK == 0
 void merit(unsigned grid, size_t smem, cudaStream_t st, const DevStruct &S, const MeritArgs &a) {

@@ -4,7 +4,9 @@
   * a non-quadratic objective over 40 (stage level) and 20 (full solve) variables (Expr.convexify degree 2,
     expr.py:143-153: numerical Hessian, eigenvalue shift -- a warp-parallel Jacobi sweep on the device);
     up to 64 variables are accepted;
-  * up to 16 constraint blocks per structure.
+  * up to 16 constraint blocks per structure;
+  * structures whose n x n system matrix exceeds one SM's shared memory (n = 240): S and its inverse live in
+    global memory and are streamed by the ADMM loop.
 """
 import numpy as np
 import pytest
@@ -165,3 +167,55 @@ def test_full_solve_with_an_objective_over_20_variables():
     xr = ref["x"]
     assert np.abs(out["x"][0].cpu().numpy() - xr).max() <= 1e-4 * max(1.0, np.abs(xr).max())
     eng.close()
+
+
+# ------------------------------------------------------------------ n beyond what one SM's shared memory holds
+BIG_T = 120  # point robot over 120 time steps: n = 240, 360 penalty rows; S = P + sigma I + A'RA is 240 x 240 = 460 KB
+
+
+@pytest.fixture(scope="module")
+def big():
+    from sco_py_b200.engine import Engine
+    st, params, x0 = W.gen_point_robot(3, T=BIG_T)
+    eng = Engine(st)
+    yield eng, st, params, x0
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_large_structure_keeps_S_in_global_memory_qp_stage(big):
+    """The n x n matrix of the reduced KKT system does not fit next to the rest of the working set: it lives in a
+    per-team global workspace and the (strided) ADMM loop streams its inverse every iteration.  Same bars as the
+    shared-memory path: identical status and iteration count, |dx| <= 1e-7."""
+    eng, st, params, x0 = big
+    assert st.n == 2 * BIG_T and 8 * st.n * st.n > 227 * 1024 > eng.smem_bytes
+    B = 2
+    f, J, b, _ = eng.convexify(params[:B], x0[:B])
+    Jn, bn = J.cpu().numpy(), b.cpu().numpy()
+    lbx, ubx = x0[:B] - 1.0, x0[:B] + 1.0
+    xq, status, iters = eng.qp_solve(params[:B], _settings(), J=J, b=b, lbx=lbx, ubx=ubx, pi=np.full(B, 10.0),
+                                     kdup=np.full(B, 1, np.int32))
+    xq, status, iters = xq.cpu().numpy(), status.cpu().numpy(), iters.cpu().numpy()
+    for i in range(B):
+        Jd = helpers.split_J(st, Jn[i])
+        bl, r0 = [], 0
+        for blk in st.blocks:
+            bl.append(bn[i, r0:r0 + blk.m])
+            r0 += blk.m
+        masks = [np.ones_like(Jb, dtype=bool) for Jb in Jd]
+        P, q, A, l, u = helpers.expand_qp(st, params[i], Jd, bl, masks, lbx[i], ubx[i], 10.0, 1)
+        res = helpers.oracle_qp(P, q, A, l, u)
+        assert status[i] == res.info.status_val and iters[i] == res.info.iter, (i, status[i], iters[i], res.info.iter)
+        assert np.abs(xq[i] - res.x).max() <= 1e-7 * max(1.0, np.abs(res.x).max())
+
+
+@pytest.mark.gpu
+def test_large_structure_full_solve_matches_port(big):
+    eng, st, params, x0 = big
+    out = eng.solve_batch(params, x0, _settings())
+    x, verdict, vio = out["x"].cpu().numpy(), out["verdict"].cpu().numpy(), out["max_vio"].cpu().numpy()
+    for i in range(x0.shape[0]):
+        ref = sqp_port.solve(st, params[i], x0[i], solver=W.SOLVER_SETTINGS)
+        assert (verdict[i] == 1) == ref["success"], (i, out["stats"][i].tolist(), ref["stats"])
+        assert np.abs(x[i] - ref["x"]).max() <= 1e-4 * max(1.0, np.abs(ref["x"]).max())
+        assert abs(vio[i] - ref["max_vio"]) <= 1e-5
