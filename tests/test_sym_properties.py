@@ -132,3 +132,55 @@ def _all(node, seen=None):
         for c in node.args:
             _all(c, seen)
     return list(seen.values())
+
+
+# ------------------------------------------------------------------ the device VM on the same random programs
+import pytest  # noqa: E402
+
+
+def _problem(rows_sym, pt, analytic):
+    from sco_py_b200.expr import BoundExpr, LEqExpr, QuadExpr, SymExpr
+    from sco_py_b200.sco_b200.osqp_utils import OSQPVar
+    from sco_py_b200.sco_b200.prob import Prob
+    from sco_py_b200.sco_b200.variable import Variable
+    prob = Prob()
+    ov = np.array([[OSQPVar("x%d" % j)] for j in range(N)], dtype=object)
+    for v in ov[:, 0]:
+        prob.add_osqp_var(v)
+    var = Variable(ov, value=np.asarray(pt, dtype=float).reshape(N, 1))
+    prob.add_var(var)
+    prob.add_obj_expr(BoundExpr(QuadExpr(np.eye(N), np.zeros((1, N)), np.zeros((1, 1))), var))
+    prob.add_cnt_expr(BoundExpr(LEqExpr(SymExpr(rows_sym, N, analytic=analytic), np.zeros((len(rows_sym), 1))), var))
+    return prob
+
+
+@pytest.mark.gpu
+@settings(max_examples=10, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(hst.lists(exprs, min_size=2, max_size=2), hst.lists(points, min_size=4, max_size=4))
+def test_device_vm_evaluates_random_programs(rows, pts):
+    """Values to 1e-10 and forward-mode Jacobians to 1e-8 of random expression DAGs (temporaries, abs / min / max, integer
+    powers) on the device against the host interpreter; affine offsets b = f - J x of the convexification."""
+    from sco_py_b200 import batch
+    from sco_py_b200.engine import Engine
+    X = sym.variables(N)
+    for r in rows:
+        for node in _all(r):
+            node._sym = None
+    try:
+        rows_sym = [r.sym(X) for r in rows]
+        prog, _ = sym.compile_rows(rows_sym)
+    except ValueError:
+        return
+    st, params, x0, _ = batch.compile_batch([_problem(rows_sym, p, True) for p in pts])
+    eng = Engine(st)
+    f, J, b, _ = [t.cpu().numpy() for t in eng.convexify(params, x0)]
+    eng.close()
+    for i, p in enumerate(pts):
+        v = np.array(p)
+        fh = sym.eval_program(prog, 2, v)
+        Jh = sym.jacobian(prog, 2, N, v)
+        scale = max(1.0, np.abs(fh).max())
+        # device libm differs from the host's in the last ulp or two; cancellation inside a random expression amplifies it
+        assert np.abs(f[i] - fh).max() <= 1e-10 * scale, (i, f[i], fh)
+        assert np.abs(J[i].reshape(2, N) - Jh).max() <= 1e-8 * max(1.0, np.abs(Jh).max()), (i, J[i], Jh)
+        assert np.abs(b[i] - (fh - Jh @ v)).max() <= 1e-8 * max(scale, np.abs(Jh).max())
