@@ -83,3 +83,27 @@ def test_result_gather_world_size_2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_reference_arm_prints_one_line_within_its_budget_single_and_under_torchrun():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm): one JSON line with the contract's
+    keys inside a wall-clock budget, also when the time runs out mid-problem; under torchrun rank 0 alone works and
+    prints, the other ranks exit 0."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SCO_REF_BUDGET_S="4")
+    for cmd in ([sys.executable, "bench.py", "--impl", "reference", "--steps", "20", "--warmup", "5", "--cpu-cores", "2"],
+                [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                 "127.0.0.1", "--master-port", "29533", "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "20",
+                 "--warmup", "5", "--cpu-cores", "2"]):
+        p = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=240)
+        assert p.returncode == 0, p.stderr[-2000:]
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        assert len(lines) == 1, p.stdout
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["metric"] == "converged SQP problems/sec" and d["unit"] == "problems/s"
+        assert d["higher_is_better"] is True and d["gpu_launches"] == 0
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2
+        assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+        assert d["detail"]["wall_s"] <= 10.0 and d["value"] >= 0.0
